@@ -1,0 +1,138 @@
+/* b2z.h -- C ABI of the B200-native STARK segment prover (libb2z.so).
+ *
+ * Drop-in boundary (seam S3): zeth reaches the prover through ONE call,
+ *     default_prover().prove(env, elf)            /root/reference/crates/host/src/lib.rs:137
+ * (configured at lib.rs:132-136, result checked at crates/host/src/bin/cli.rs:103-107).  Below that call the
+ * un-vendored risc0 crates drive a `Hal` / `CircuitHal` back-end whose CUDA implementation crosses an
+ * `extern "C"` boundary into risc0-sys kernels.  This header is that boundary for the B200 back-end: plain
+ * pointers and sizes, no C++ / torch types.  Each entry point names the upstream trait method it replaces
+ * (risc0-zkp 3.0.2 `hal/mod.rs` trait Hal, `prove/*.rs`; risc0-circuit-rv32im 4.0.2 CircuitHal), which is what a
+ * Rust `impl Hal for B200Hal` shim binds.
+ *
+ * Conventions (same as upstream's FFI): every function returns NULL on success or a static/thread-local,
+ * NUL-terminated error string (do not free).  Field elements are u32 Montgomery words < P = 15*2^27+1; matrices
+ * are column-major [cols][rows]; ext elements are 4 consecutive words; digests are 8 words.  All `dev` pointers
+ * are device pointers of the context's device; work is enqueued on the context's stream and is asynchronous
+ * unless stated.  A context is single-threaded (upstream `Rc<dyn Prover>` is !Send): one context per thread.
+ * There is NO CPU fallback: without a usable CUDA device every compute entry point returns an error.
+ */
+#ifndef B2Z_H
+#define B2Z_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b2z_ctx b2z_ctx;
+typedef struct b2z_circuit b2z_circuit;
+typedef const char* b2z_err;
+
+/* protocol constants (risc0-zkp 3.0.2 src/lib.rs) */
+#define B2Z_INV_RATE 4
+#define B2Z_QUERIES 50
+#define B2Z_FRI_FOLD 16
+#define B2Z_FRI_MIN_DEGREE 256
+#define B2Z_EXT_SIZE 4
+#define B2Z_CHECK_SIZE 16
+#define B2Z_DIGEST_WORDS 8
+#define B2Z_ZK_CYCLES 1994
+#define B2Z_GROUP_ACCUM 0
+#define B2Z_GROUP_CODE 1
+#define B2Z_GROUP_DATA 2
+
+/* ---- context / memory: replaces CudaHal::new + Buffer alloc / copy_from / view (hal/cuda.rs) ---- */
+const char* b2z_version(void);
+b2z_err b2z_init(int device, b2z_ctx** out);
+b2z_err b2z_destroy(b2z_ctx* ctx);
+/* adopt an externally owned cudaStream_t (e.g. torch.cuda.Stream().cuda_stream); NULL restores the own stream */
+b2z_err b2z_set_stream(b2z_ctx* ctx, void* cuda_stream);
+b2z_err b2z_sync(b2z_ctx* ctx);
+b2z_err b2z_alloc(b2z_ctx* ctx, size_t bytes, void** dev);
+b2z_err b2z_free(b2z_ctx* ctx, void* dev);
+b2z_err b2z_h2d(b2z_ctx* ctx, void* dev, const void* host, size_t bytes);
+b2z_err b2z_d2h(b2z_ctx* ctx, void* host, const void* dev, size_t bytes); /* synchronises */
+/* number of kernels this context has launched since creation (bench.py `gpu_launches`) */
+uint64_t b2z_launch_count(const b2z_ctx* ctx);
+
+/* ---- Hal operations (trait Hal, risc0-zkp hal/mod.rs; CPU semantics in hal/cpu.rs) ---- */
+/* Hal::batch_interpolate_ntt(io, count): natural evaluations -> bit-reversed coefficients, scaled by 1/n */
+b2z_err b2z_batch_interpolate_ntt(b2z_ctx* ctx, uint32_t* io, size_t count, unsigned po2);
+/* Hal::batch_evaluate_ntt(io, count, expand_bits): bit-reversed coefficients -> natural evaluations */
+b2z_err b2z_batch_evaluate_ntt(b2z_ctx* ctx, uint32_t* io, size_t count, unsigned po2, unsigned expand_bits);
+/* Hal::batch_expand_into_evaluate_ntt(out, in, count, expand_bits): out[i] = in[i >> bits], remaining layers */
+b2z_err b2z_batch_expand_into_evaluate_ntt(b2z_ctx* ctx, uint32_t* out, const uint32_t* in, size_t count, unsigned in_po2,
+                                           unsigned expand_bits);
+/* Hal::batch_bit_reverse(io, count) */
+b2z_err b2z_batch_bit_reverse(b2z_ctx* ctx, uint32_t* io, size_t count, unsigned po2);
+/* Hal::zk_shift(io, count): bit-reversed slot j *= 3^rev(j) */
+b2z_err b2z_zk_shift(b2z_ctx* ctx, uint32_t* io, size_t count, unsigned po2);
+/* Hal::hash_rows(output, matrix): Poseidon2 sponge of every row of a column-major [cols][rows] matrix */
+b2z_err b2z_hash_rows(b2z_ctx* ctx, uint32_t* out_digests, const uint32_t* matrix, size_t rows, size_t cols);
+/* Hal::hash_fold(io, input_size, output_size): node[out+j] = hash_pair(node[in+2j], node[in+2j+1]) */
+b2z_err b2z_hash_fold(b2z_ctx* ctx, uint32_t* nodes, size_t in_size, size_t out_size);
+/* MerkleTreeProver::new (prove/merkle.rs): hash_rows into nodes[rows..2rows) then every hash_fold layer */
+b2z_err b2z_merkle_build(b2z_ctx* ctx, uint32_t* nodes, const uint32_t* matrix, size_t rows, size_t cols);
+/* Hal::fri_fold(output, input, mix): mix = 4 host words */
+b2z_err b2z_fri_fold(b2z_ctx* ctx, uint32_t* out, const uint32_t* in, const uint32_t* mix_host, size_t out_count);
+/* Hal::batch_evaluate_any(coeffs, poly_count, which, xs, out): which/xs/out are device arrays */
+b2z_err b2z_batch_evaluate_any(b2z_ctx* ctx, const uint32_t* coeffs, size_t poly_count, unsigned po2, const uint32_t* which,
+                               const uint32_t* xs, size_t eval_count, uint32_t* out);
+/* Hal::mix_poly_coeffs(output, mix_start, mix, input, combos, input_size, count); mix values are host words */
+b2z_err b2z_mix_poly_coeffs(b2z_ctx* ctx, uint32_t* out, const uint32_t* mix_start_host, const uint32_t* mix_host,
+                            const uint32_t* in, const uint32_t* combos_dev, size_t input_size, size_t count);
+/* Hal::eltwise_add_elem / eltwise_sum_extelem / eltwise_copy_elem / eltwise_zeroize_elem */
+b2z_err b2z_eltwise_add_elem(b2z_ctx* ctx, uint32_t* out, const uint32_t* a, const uint32_t* b, size_t n);
+b2z_err b2z_eltwise_sum_extelem(b2z_ctx* ctx, uint32_t* out, const uint32_t* in, size_t count, size_t to_add);
+b2z_err b2z_eltwise_copy_elem(b2z_ctx* ctx, uint32_t* out, const uint32_t* in, size_t n);
+b2z_err b2z_eltwise_zeroize_elem(b2z_ctx* ctx, uint32_t* io, size_t n);
+/* Hal::gather_sample(dst, src, idx, size, stride) */
+b2z_err b2z_gather_sample(b2z_ctx* ctx, uint32_t* dst, const uint32_t* src, size_t idx, size_t size, size_t stride);
+/* core/poly.rs poly_divide applied to an ext coefficient array on the device (prover.rs runs it on the CPU):
+ * in-place synthetic division of `count` AoS ext coefficients by (X - z); remainder -> 4 host words */
+b2z_err b2z_poly_divide(b2z_ctx* ctx, uint32_t* ext_coeffs, size_t count, const uint32_t* z_host, uint32_t* remainder_host);
+
+/* ---- circuit: taps + constraint program (risc0-zkp taps.rs / adapter.rs PolyExtStep), as a blob ---- */
+b2z_err b2z_circuit_load(b2z_ctx* ctx, const uint32_t* blob, size_t words, b2z_circuit** out);
+/* CPU-side build step: generate + NVRTC-compile the circuit kernels into the on-disk cubin cache (no GPU needed) */
+b2z_err b2z_circuit_precompile(const uint32_t* blob, size_t words);
+b2z_err b2z_circuit_free(b2z_circuit* c);
+size_t b2z_circuit_group_size(const b2z_circuit* c, int group);
+size_t b2z_circuit_globals_size(const b2z_circuit* c);
+size_t b2z_circuit_mix_size(const b2z_circuit* c);
+size_t b2z_circuit_seal_words(const b2z_circuit* c, unsigned po2);
+/* generated CUDA source of the circuit kernels (NUL-terminated; owned by the circuit) */
+const char* b2z_circuit_source(const b2z_circuit* c);
+/* CircuitHal::eval_check(check, groups, globals, poly_mix, po2, steps): groups = device LDE matrices in order
+ * accum, code, data; globals/mix device arrays; poly_mix = 4 host words */
+b2z_err b2z_eval_check(b2z_ctx* ctx, const b2z_circuit* c, uint32_t* check, const uint32_t* const groups_dev[3],
+                       const uint32_t* globals_dev, const uint32_t* mix_dev, const uint32_t* poly_mix_host, unsigned po2);
+/* CircuitHal::accumulate (synthetic-circuit form: ext running sums fed by the Fiat-Shamir mix) */
+b2z_err b2z_accumulate(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, uint32_t* accum, const uint32_t* code,
+                       const uint32_t* data, const uint32_t* mix_dev, const uint32_t* accum_noise_dev, size_t zk_rows);
+/* witness generation for synthetic circuits (the reference's witgen / step_exec stage): fills code, data, globals */
+b2z_err b2z_witgen(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, uint32_t* code, uint32_t* data, uint32_t* globals_dev,
+                   uint32_t* accum_noise_dev, uint64_t seed, size_t zk_rows);
+
+/* ---- segment prover: replaces SegmentProver::prove -> seal: Vec<u32> (risc0-circuit-rv32im prove/) ---- */
+/* Witness already resident in HBM (device pointers). seal_host must hold b2z_circuit_seal_words() words. Synchronises. */
+b2z_err b2z_prove_segment_device(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, const uint32_t* code_dev,
+                                 const uint32_t* data_dev, const uint32_t* globals_host, const uint32_t* accum_noise_dev,
+                                 size_t zk_rows, uint32_t* seal_host, size_t* seal_words);
+/* Host buffers in, seal out: H2D of the witness and D2H of the seal happen inside the call. */
+b2z_err b2z_prove_segment(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, const uint32_t* code_host, const uint32_t* data_host,
+                          const uint32_t* globals_host, const uint32_t* accum_noise_host, size_t zk_rows, uint32_t* seal_host,
+                          size_t* seal_words);
+/* per-phase device milliseconds of the last prove call on this context (names via b2z_phase_name; returns count) */
+size_t b2z_last_phase_ms(const b2z_ctx* ctx, double* ms, size_t cap);
+const char* b2z_phase_name(size_t i);
+
+/* host-side Poseidon2 (transcript) helpers, exported for tests: hash_elem_slice / hash_pair / permutation */
+void b2z_host_poseidon2_mix(uint32_t* state24);
+void b2z_host_hash_elem_slice(const uint32_t* elems, size_t n, uint32_t* digest8);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,178 @@
+"""Op-by-op parity of the CUDA Hal (through the C ABI) against the CPU oracle -- the `dual` HAL pattern of
+risc0-zkp hal/dual.rs: same seeded inputs, every output word must be identical."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+P = 15 * (1 << 27) + 1
+
+
+def rand_fp(rng, n):
+    return rng.integers(0, P, size=n, dtype=np.uint64).astype(np.uint32)
+
+
+@pytest.mark.parametrize("po2,count", [(1, 3), (4, 5), (9, 7), (13, 3), (14, 2), (16, 3), (18, 2), (20, 1)])
+def test_batch_interpolate_ntt(hal, oracle, po2, count):
+    rng = np.random.default_rng(100 + po2)
+    x = rand_fp(rng, count << po2)
+    d = hal.copy_from(x)
+    hal.batch_interpolate_ntt(d, count, po2)
+    got = hal.view(d, x.size)
+    hal.free(d)
+    assert np.array_equal(got, oracle.batch_interpolate_ntt(x, count))
+
+
+@pytest.mark.parametrize("po2,count", [(2, 3), (7, 5), (11, 7), (12, 2), (14, 3), (16, 2), (18, 1)])
+def test_batch_expand_into_evaluate_ntt(hal, oracle, po2, count):
+    rng = np.random.default_rng(200 + po2)
+    x = rand_fp(rng, count << po2)
+    d = hal.copy_from(x)
+    o = hal.alloc(count << (po2 + 2))
+    hal.batch_expand_into_evaluate_ntt(o, d, count, po2, 2)
+    got = hal.view(o, count << (po2 + 2))
+    hal.free(d)
+    hal.free(o)
+    assert np.array_equal(got, oracle.batch_expand_into_evaluate_ntt(x, count, 2))
+
+
+@pytest.mark.parametrize("po2,count", [(3, 2), (10, 3), (15, 2), (17, 1)])
+def test_batch_evaluate_ntt_roundtrip(hal, oracle, po2, count):
+    rng = np.random.default_rng(300 + po2)
+    x = rand_fp(rng, count << po2)
+    d = hal.copy_from(x)
+    hal.batch_interpolate_ntt(d, count, po2)
+    hal.batch_evaluate_ntt(d, count, po2, 0)
+    got = hal.view(d, x.size)
+    hal.free(d)
+    assert np.array_equal(got, x)  # iNTT then NTT is the identity
+    assert np.array_equal(oracle.batch_evaluate_ntt(oracle.batch_interpolate_ntt(x, count), count, 0), x)
+
+
+@pytest.mark.parametrize("po2,count", [(1, 2), (8, 3), (13, 5), (16, 2)])
+def test_bit_reverse_and_zk_shift(hal, oracle, po2, count):
+    rng = np.random.default_rng(400 + po2)
+    x = rand_fp(rng, count << po2)
+    d = hal.copy_from(x)
+    hal.batch_bit_reverse(d, count, po2)
+    assert np.array_equal(hal.view(d, x.size), oracle.batch_bit_reverse(x, count))
+    hal.batch_bit_reverse(d, count, po2)
+    hal.zk_shift(d, count, po2)
+    assert np.array_equal(hal.view(d, x.size), oracle.zk_shift(x, count))
+    hal.free(d)
+
+
+@pytest.mark.parametrize("rows,cols", [(16, 1), (64, 15), (256, 16), (512, 17), (1024, 64), (4096, 200), (8, 0)])
+def test_hash_rows(hal, oracle, rows, cols):
+    rng = np.random.default_rng(500 + rows + cols)
+    m = rand_fp(rng, rows * cols)
+    d = hal.copy_from(m if m.size else np.zeros(1, dtype=np.uint32))
+    o = hal.alloc(rows * 8)
+    hal.hash_rows(o, d, rows, cols)
+    got = hal.view(o, rows * 8)
+    hal.free(d)
+    hal.free(o)
+    assert np.array_equal(got, oracle.hash_rows(m, rows, cols))
+
+
+@pytest.mark.parametrize("rows,cols", [(64, 5), (2048, 33)])
+def test_merkle_build(hal, oracle, rows, cols):
+    rng = np.random.default_rng(600 + rows)
+    m = rand_fp(rng, rows * cols)
+    d = hal.copy_from(m)
+    nodes = hal.copy_from(np.zeros(2 * rows * 8, dtype=np.uint32))
+    hal.merkle_build(nodes, d, rows, cols)
+    got = hal.view(nodes, 2 * rows * 8)
+    want = oracle.merkle_nodes(m, rows, cols)
+    hal.free(d)
+    hal.free(nodes)
+    assert np.array_equal(got[8:], want[8:])  # node 0 is unused
+
+
+@pytest.mark.parametrize("count", [1, 16, 1000, 4096])
+def test_fri_fold(hal, oracle, count):
+    rng = np.random.default_rng(700 + count)
+    x = rand_fp(rng, 4 * 16 * count)
+    mix = rand_fp(rng, 4)
+    d = hal.copy_from(x)
+    o = hal.alloc(4 * count)
+    hal.fri_fold(o, d, mix, count)
+    got = hal.view(o, 4 * count)
+    hal.free(d)
+    hal.free(o)
+    assert np.array_equal(got, oracle.fri_fold(x, mix))
+
+
+@pytest.mark.parametrize("po2,polys,evals", [(4, 3, 5), (12, 6, 9), (16, 4, 20)])
+def test_batch_evaluate_any(hal, oracle, po2, polys, evals):
+    rng = np.random.default_rng(800 + po2)
+    coeffs = rand_fp(rng, polys << po2)
+    which = rng.integers(0, polys, size=evals).astype(np.uint32)
+    xs = rand_fp(rng, 4 * evals)
+    dc, dw, dx = hal.copy_from(coeffs), hal.copy_from(which), hal.copy_from(xs)
+    o = hal.alloc(4 * evals)
+    hal.batch_evaluate_any(dc, polys, po2, dw, dx, evals, o)
+    got = hal.view(o, 4 * evals)
+    for p in (dc, dw, dx, o):
+        hal.free(p)
+    assert np.array_equal(got, oracle.batch_evaluate_any(coeffs, polys, which, xs))
+
+
+@pytest.mark.parametrize("po2,cols,ncombos", [(5, 7, 3), (12, 40, 4), (14, 20, 11)])
+def test_mix_poly_coeffs(hal, oracle, po2, cols, ncombos):
+    rng = np.random.default_rng(900 + po2)
+    n = 1 << po2
+    inp = rand_fp(rng, cols * n)
+    combos = rng.integers(0, ncombos, size=cols).astype(np.uint32)
+    out0 = rand_fp(rng, 4 * n * ncombos)
+    ms, mix = rand_fp(rng, 4), rand_fp(rng, 4)
+    do, di, dcm = hal.copy_from(out0), hal.copy_from(inp), hal.copy_from(combos)
+    hal.mix_poly_coeffs(do, ms, mix, di, dcm, cols, n)
+    got = hal.view(do, out0.size)
+    for p in (do, di, dcm):
+        hal.free(p)
+    assert np.array_equal(got, oracle.mix_poly_coeffs(out0, ms, mix, inp, combos, n))
+
+
+def test_eltwise_and_gather(hal, oracle):
+    rng = np.random.default_rng(1000)
+    n = 5000
+    a, b = rand_fp(rng, n), rand_fp(rng, n)
+    da, db = hal.copy_from(a), hal.copy_from(b)
+    o = hal.alloc(n)
+    hal.eltwise_add_elem(o, da, db, n)
+    assert np.array_equal(hal.view(o, n), ((a.astype(np.uint64) + b) % P).astype(np.uint32))
+    ext = rand_fp(rng, 4 * 3 * 1000)
+    de = hal.copy_from(ext)
+    o2 = hal.alloc(4000)
+    hal.eltwise_sum_extelem(o2, de, 1000, 3)
+    assert np.array_equal(hal.view(o2, 4000), oracle.eltwise_sum_extelem(ext, 1000))
+    z = a.copy()
+    z[::7] = 0xFFFFFFFF
+    dz = hal.copy_from(z)
+    hal.eltwise_zeroize_elem(dz, n)
+    assert np.array_equal(hal.view(dz, n), oracle.eltwise_zeroize_elem(z))
+    g = hal.alloc(40)
+    hal.gather_sample(g, da, 17, 40, 100)
+    assert np.array_equal(hal.view(g, 40), a[17::100][:40])
+    hal.eltwise_copy_elem(o, db, n)
+    assert np.array_equal(hal.view(o, n), b)
+    for p in (da, db, o, de, o2, dz, g):
+        hal.free(p)
+
+
+@pytest.mark.parametrize("count", [1, 7, 2048, 2049, 100000])
+def test_poly_divide(hal, oracle, count):
+    """q = p / (X - z): check q*(X - z) + r == p coefficient-wise with oracle ext arithmetic."""
+    rng = np.random.default_rng(1100 + count)
+    p = rand_fp(rng, 4 * count)
+    z = rand_fp(rng, 4)
+    d = hal.copy_from(p)
+    rem = hal.poly_divide(d, count, z)
+    q = hal.view(d, 4 * count).reshape(count, 4)
+    hal.free(d)
+    zq = oracle.fp4_mul(np.tile(z, count), q.reshape(-1)).reshape(count, 4).astype(np.int64)
+    # p[i] = q[i-1] - z*q[i]  (q[-1] = 0, top quotient coefficient is 0) ; p[0] = r - z*q[0]
+    shifted = np.vstack([rem.reshape(1, 4), q[:-1]]).astype(np.int64)
+    recon = (shifted - zq) % P
+    assert np.array_equal(recon.astype(np.uint32), p.reshape(count, 4))
+    assert not q[-1].any()

@@ -1,0 +1,81 @@
+"""Whole-segment parity: the seal produced by the CUDA pipeline (through the C ABI) must be word-for-word the
+oracle's seal on the same cached witness, must verify, and a tampered seal must be rejected."""
+import numpy as np
+import pytest
+
+from zeth_b200 import hal as H
+from zeth_b200 import synth_circuit as S
+
+pytestmark = pytest.mark.gpu
+
+
+def _witness(oracle, sc, po2, seed):
+    oc = oracle.Circuit(sc.blob)
+    n = 1 << po2
+    zk = min(1994, n // 4)
+    code, data, glob, noise = oc.witgen(po2, seed, zk)
+    return oc, code, data, glob, noise, zk
+
+
+@pytest.mark.parametrize("mk,po2", [(S.circuit_tiny, 6), (S.circuit_tiny, 9), (S.circuit_small, 12), (S.circuit_small, 14)])
+def test_seal_parity_host_api(hal, oracle, mk, po2):
+    sc = mk()
+    oc, code, data, glob, noise, zk = _witness(oracle, sc, po2, 11 + po2)
+    want = oc.prove(po2, code, data, glob, noise, zk)
+    c = H.Circuit(hal, sc.blob)
+    got = hal.prove_segment(c, po2, code, data, glob, noise, zk)
+    assert got.size == want.size
+    diff = np.nonzero(got != want)[0]
+    assert diff.size == 0, f"first differing seal word {diff[:5]} of {want.size}"
+    assert oc.verify(got) == 0
+    bad = got.copy()
+    bad[bad.size // 3] ^= 1
+    assert oc.verify(bad) != 0
+    c.close()
+
+
+def test_witgen_accumulate_eval_check_parity(hal, oracle):
+    sc = S.circuit_small()
+    po2 = 11
+    oc, code, data, glob, noise, zk = _witness(oracle, sc, po2, 77)
+    n = 1 << po2
+    wa, wc, wd = sc.group_sizes
+    c = H.Circuit(hal, sc.blob)
+    dcode, ddata = hal.alloc(wc * n), hal.alloc(wd * n)
+    dglob, dnoise = hal.alloc(sc.globals_size), hal.alloc(wa * zk)
+    hal.witgen(c, po2, dcode, ddata, dglob, dnoise, 77, zk)
+    assert np.array_equal(hal.view(dcode, wc * n), code)
+    assert np.array_equal(hal.view(ddata, wd * n), data)
+    assert np.array_equal(hal.view(dglob, sc.globals_size), glob)
+    assert np.array_equal(hal.view(dnoise, wa * zk), noise)
+    rng = np.random.default_rng(5)
+    mix = rng.integers(0, 15 * (1 << 27) + 1, size=sc.mix_size, dtype=np.uint64).astype(np.uint32)
+    dmix = hal.copy_from(mix)
+    daccum = hal.alloc(wa * n)
+    hal.accumulate(c, po2, daccum, dcode, ddata, dmix, dnoise, zk)
+    accum = oc.accumulate(po2, code, data, mix, noise, zk)
+    assert np.array_equal(hal.view(daccum, wa * n), accum)
+    # eval_check on LDEs of the three groups
+    groups_h = [oracle.batch_expand_into_evaluate_ntt(oracle.zk_shift(oracle.batch_interpolate_ntt(g, w), w), w, 2)
+                for g, w in ((accum, wa), (code, wc), (data, wd))]
+    dgs = [hal.copy_from(g) for g in groups_h]
+    pm = rng.integers(0, 15 * (1 << 27) + 1, size=4, dtype=np.uint64).astype(np.uint32)
+    dcheck = hal.alloc(16 * n)
+    hal.eval_check(c, dcheck, dgs, dglob, dmix, pm, po2)
+    want = oc.eval_check(po2, groups_h, glob, mix, pm)
+    assert np.array_equal(hal.view(dcheck, 16 * n), want)
+    c.close()
+
+
+def test_seal_parity_device_api_planning_circuit(hal, oracle):
+    """BASELINE config-2 shape (W = 16 + 192 + 48) at a size the oracle proves in seconds."""
+    sc = S.circuit_planning()
+    po2 = 12
+    oc, code, data, glob, noise, zk = _witness(oracle, sc, po2, 0xB2000002)
+    want = oc.prove(po2, code, data, glob, noise, zk)
+    c = H.Circuit(hal, sc.blob)
+    dcode, ddata, dnoise = hal.copy_from(code), hal.copy_from(data), hal.copy_from(noise)
+    got = hal.prove_segment_device(c, po2, dcode, ddata, glob, dnoise, zk)
+    assert np.array_equal(got, want)
+    assert oc.verify(got) == 0
+    c.close()

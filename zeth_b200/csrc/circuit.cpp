@@ -1,0 +1,461 @@
+// Circuit blob parsing, TapSet derivation, CUDA code generation for the constraint program and NVRTC loading.
+//
+// Shape follows risc0-zkp 3.0.2 taps.rs (TapSet: taps sorted by (group, offset, back); registers; combos) and
+// adapter.rs (PolyExtStep program) -- SURVEY.md Appendix A.7.  Upstream ships the rv32im program as *generated*
+// CUDA (risc0-circuit-rv32im-sys kernels/cuda/eval_check*.cu).  Here the generator is part of the library: the
+// program arrives as data (circuit blob), is specialised into one straight-line sm_100a kernel by NVRTC (cached on
+// disk as a cubin keyed by the source hash) and loaded with cudaLibraryLoadData.
+#include "circuit.h"
+
+#include <dlfcn.h>
+#include <sys/stat.h>
+
+#include <algorithm>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+
+namespace b2z {
+
+static thread_local std::string g_err;
+const char* set_error(const std::string& msg) {
+  g_err = msg;
+  return g_err.c_str();
+}
+
+static int cmp_backs(const uint32_t* a, size_t na, const uint32_t* b, size_t nb) {
+  size_t n = na < nb ? na : nb;
+  for (size_t i = 0; i < n; i++)
+    if (a[i] != b[i]) return a[i] < b[i] ? -1 : 1;
+  return na == nb ? 0 : (na < nb ? -1 : 1);
+}
+
+b2z_err circuit_parse(b2z_circuit* c, const uint32_t* blob, size_t words) {
+  B2Z_REQUIRE(words >= 24 && blob[0] == 0x435a3242u && blob[1] == 1, "circuit blob: bad magic/version");
+  for (int g = 0; g < 3; g++) c->group_size[g] = blob[2 + g];
+  c->globals_size = blob[5];
+  c->mix_size = blob[6];
+  c->n_taps = blob[7];
+  size_t n_steps = blob[8];
+  c->ret = blob[9];
+  memcpy(c->info, blob + 10, 16);
+  size_t n_wit_steps = blob[14], n_wit_stores = blob[15], n_accum = blob[16], n_pins = blob[17];
+  size_t pos = 24;
+  size_t need = pos + c->n_taps + 5 * n_steps + 5 * n_wit_steps + 2 * n_wit_stores + n_accum + 2 * n_pins + c->group_size[2];
+  B2Z_REQUIRE(words >= need, "circuit blob: truncated");
+  for (size_t i = 0; i < c->n_taps; i++) {
+    uint32_t w = blob[pos++];
+    c->tap_offset.push_back(w & 0xffff);
+    c->tap_back.push_back((w >> 16) & 0xff);
+    c->tap_group.push_back(w >> 24);
+    B2Z_REQUIRE((w >> 24) < 3 && (w & 0xffff) < c->group_size[w >> 24], "circuit blob: tap out of range");
+  }
+  auto read_steps = [&](std::vector<b2z_circuit::Step>& v, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+      v.push_back({blob[pos], blob[pos + 1], blob[pos + 2], blob[pos + 3], blob[pos + 4]});
+      pos += 5;
+    }
+  };
+  read_steps(c->steps, n_steps);
+  read_steps(c->wit_steps, n_wit_steps);
+  for (size_t i = 0; i < n_wit_stores; i++) {
+    c->wit_store_col.push_back(blob[pos++]);
+    c->wit_store_var.push_back(blob[pos++]);
+  }
+  for (size_t i = 0; i < n_accum; i++) c->accum_col.push_back(blob[pos++]);
+  for (size_t i = 0; i < n_pins; i++) {
+    c->pin_col.push_back(blob[pos++]);
+    c->pin_global.push_back(blob[pos++]);
+  }
+  for (size_t i = 0; i < c->group_size[2]; i++) c->col_kind.push_back((uint8_t)blob[pos++]);
+  B2Z_REQUIRE(c->mix_size >= 4 * n_accum, "circuit blob: mix too small for the accumulators");
+  B2Z_REQUIRE(c->group_size[0] >= 4 * n_accum, "circuit blob: accum group too small");
+
+  // registers
+  for (size_t i = 0; i < c->n_taps;) {
+    size_t j = i;
+    while (j < c->n_taps && c->tap_group[j] == c->tap_group[i] && c->tap_offset[j] == c->tap_offset[i]) j++;
+    if (i > 0) {
+      bool ordered = c->tap_group[i] > c->tap_group[i - 1] || (c->tap_group[i] == c->tap_group[i - 1] && c->tap_offset[i] > c->tap_offset[i - 1]);
+      B2Z_REQUIRE(ordered, "circuit blob: taps not sorted by (group, offset, back)");
+    }
+    c->reg_group.push_back(c->tap_group[i]);
+    c->reg_offset.push_back(c->tap_offset[i]);
+    c->reg_tap_pos.push_back((uint32_t)i);
+    c->reg_size.push_back((uint32_t)(j - i));
+    i = j;
+  }
+  size_t nr = c->reg_group.size();
+  // every column of every group must be a register (all columns are opened by DEEP)
+  {
+    size_t r = 0;
+    for (int g = 0; g < 3; g++)
+      for (size_t col = 0; col < c->group_size[g]; col++, r++)
+        B2Z_REQUIRE(r < nr && c->reg_group[r] == (uint32_t)g && c->reg_offset[r] == col, "circuit blob: a column has no tap");
+    B2Z_REQUIRE(r == nr, "circuit blob: register count mismatch");
+  }
+  // combos in lexicographic order of their back-lists
+  std::vector<uint32_t> uniq;
+  for (size_t r = 0; r < nr; r++) {
+    const uint32_t* b = &c->tap_back[c->reg_tap_pos[r]];
+    bool found = false;
+    for (uint32_t u : uniq)
+      if (cmp_backs(b, c->reg_size[r], &c->tap_back[c->reg_tap_pos[u]], c->reg_size[u]) == 0) found = true;
+    if (!found) uniq.push_back((uint32_t)r);
+  }
+  std::sort(uniq.begin(), uniq.end(), [&](uint32_t x, uint32_t y) {
+    return cmp_backs(&c->tap_back[c->reg_tap_pos[x]], c->reg_size[x], &c->tap_back[c->reg_tap_pos[y]], c->reg_size[y]) < 0;
+  });
+  c->n_combos = uniq.size();
+  size_t tot = 0;
+  for (uint32_t u : uniq) {
+    c->combo_begin.push_back((uint32_t)tot);
+    for (uint32_t k = 0; k < c->reg_size[u]; k++) c->combo_backs.push_back(c->tap_back[c->reg_tap_pos[u] + k]);
+    tot += c->reg_size[u];
+  }
+  c->combo_begin.push_back((uint32_t)tot);
+  c->tot_combo_backs = tot;
+  c->reg_combo.resize(nr);
+  for (size_t r = 0; r < nr; r++)
+    for (size_t k = 0; k < c->n_combos; k++)
+      if (cmp_backs(&c->tap_back[c->reg_tap_pos[r]], c->reg_size[r], &c->combo_backs[c->combo_begin[k]],
+                    c->combo_begin[k + 1] - c->combo_begin[k]) == 0)
+        c->reg_combo[r] = (uint32_t)k;
+
+  // static typing
+  size_t nf = 0, nm = 0;
+  for (const auto& s : c->steps) {
+    switch (s.op) {
+      case OP_CONST: case OP_GET: case OP_GET_GLOBAL: c->fp_is_ext.push_back(0); nf++; break;
+      case OP_CONST_EXT: c->fp_is_ext.push_back(1); nf++; break;
+      case OP_ADD: case OP_SUB: case OP_MUL:
+        B2Z_REQUIRE(s.a < nf && s.b < nf, "circuit blob: forward reference");
+        c->fp_is_ext.push_back(c->fp_is_ext[s.a] | c->fp_is_ext[s.b]); nf++; break;
+      case OP_TRUE: c->mix_exp.push_back(0); nm++; break;
+      case OP_AND_EQZ:
+        B2Z_REQUIRE(s.a < nm && s.b < nf, "circuit blob: forward reference");
+        c->mix_exp.push_back(c->mix_exp[s.a] + 1); nm++; break;
+      case OP_AND_COND:
+        B2Z_REQUIRE(s.a < nm && s.b < nf && s.c < nm, "circuit blob: forward reference");
+        c->mix_exp.push_back(c->mix_exp[s.a] + c->mix_exp[s.c]); nm++; break;
+      default: return set_error("circuit blob: unknown op");
+    }
+    if (s.op == OP_GET) B2Z_REQUIRE(s.a < c->n_taps, "circuit blob: tap index out of range");
+  }
+  B2Z_REQUIRE(c->ret < nm, "circuit blob: ret out of range");
+  c->max_exp = 0;
+  for (uint32_t e : c->mix_exp) c->max_exp = std::max<size_t>(c->max_exp, e);
+  return nullptr;
+}
+
+// Seal length (words) for a given po2 -- the layout of prove/write_iop.rs + merkle.rs + fri.rs.
+static void merkle_params(size_t rows, size_t& layers, size_t& top_size) {
+  layers = ilog2(rows);
+  size_t top_layer = 0;
+  for (size_t i = 1; i < layers; i++) {
+    if (((size_t)1 << i) > B2Z_QUERIES) break;
+    top_layer = i;
+  }
+  top_size = (size_t)1 << top_layer;
+}
+size_t circuit_seal_words(const b2z_circuit* c, unsigned po2) {
+  size_t n = (size_t)1 << po2, domain = 4 * n;
+  size_t words = c->globals_size + 1;
+  size_t layers, top;
+  merkle_params(domain, layers, top);
+  size_t path = 8 * (layers - ilog2(top));
+  words += 4 * 8 * top;                         // code, data, accum, check top layers
+  words += 4 * (c->n_taps + B2Z_CHECK_SIZE);    // coeff_u
+  size_t per_query = c->group_size[0] + c->group_size[1] + c->group_size[2] + B2Z_CHECK_SIZE + 4 * path;
+  size_t size = n, dom = domain;
+  while (size > B2Z_FRI_MIN_DEGREE) {
+    size_t rows = dom / B2Z_FRI_FOLD, l2, t2;
+    merkle_params(rows, l2, t2);
+    words += 8 * t2;
+    per_query += 64 + 8 * (l2 - ilog2(t2));
+    size /= B2Z_FRI_FOLD;
+    dom /= B2Z_FRI_FOLD;
+  }
+  words += 4 * size;  // final coefficients
+  words += B2Z_QUERIES * per_query;
+  return words;
+}
+
+// ---------------- code generation ----------------
+static const char* PRELUDE = R"CUDA(
+// generated by libb2z circuit_codegen -- BabyBear field prelude (same reduction sequence as csrc/field.cuh)
+typedef unsigned int u32;
+typedef unsigned long long u64;
+#define P 2013265921u
+#define PINV 0x88000001u
+#define BETA 0x37ffffe9u
+__device__ __forceinline__ u32 fadd(u32 a, u32 b) { u32 r = a + b; return min(r, r - P); }
+__device__ __forceinline__ u32 fsub(u32 a, u32 b) { u32 r = a - b; return min(r, r + P); }
+__device__ __forceinline__ u32 fmul(u32 a, u32 b) {
+  u64 t = (u64)a * b; u32 m = (u32)t * PINV; u32 u = __umulhi(m, P); u32 r = (u32)(t >> 32) - u; return min(r, r + P);
+}
+struct E { u32 a, b, c, d; };
+__device__ __forceinline__ E emake(u32 a, u32 b, u32 c, u32 d) { E r; r.a = a; r.b = b; r.c = c; r.d = d; return r; }
+__device__ __forceinline__ E eadd(E x, E y) { return emake(fadd(x.a, y.a), fadd(x.b, y.b), fadd(x.c, y.c), fadd(x.d, y.d)); }
+__device__ __forceinline__ E esub(E x, E y) { return emake(fsub(x.a, y.a), fsub(x.b, y.b), fsub(x.c, y.c), fsub(x.d, y.d)); }
+__device__ __forceinline__ E eaddf(E x, u32 y) { return emake(fadd(x.a, y), x.b, x.c, x.d); }
+__device__ __forceinline__ E esubf(E x, u32 y) { return emake(fsub(x.a, y), x.b, x.c, x.d); }
+__device__ __forceinline__ E fsube(u32 x, E y) { return emake(fsub(x, y.a), fsub(0u, y.b), fsub(0u, y.c), fsub(0u, y.d)); }
+__device__ __forceinline__ E emulf(E x, u32 y) { return emake(fmul(x.a, y), fmul(x.b, y), fmul(x.c, y), fmul(x.d, y)); }
+__device__ __forceinline__ E emul(E x, E y) {
+  E r;
+  r.a = fadd(fmul(x.a, y.a), fmul(BETA, fadd(fadd(fmul(x.b, y.d), fmul(x.c, y.c)), fmul(x.d, y.b))));
+  r.b = fadd(fadd(fmul(x.a, y.b), fmul(x.b, y.a)), fmul(BETA, fadd(fmul(x.c, y.d), fmul(x.d, y.c))));
+  r.c = fadd(fadd(fadd(fmul(x.a, y.c), fmul(x.b, y.b)), fmul(x.c, y.a)), fmul(BETA, fmul(x.d, y.d)));
+  r.d = fadd(fadd(fmul(x.a, y.d), fmul(x.b, y.c)), fadd(fmul(x.c, y.b), fmul(x.d, y.a)));
+  return r;
+}
+__device__ __forceinline__ E eld(const u32* p) { uint4 v = *reinterpret_cast<const uint4*>(p); return emake(v.x, v.y, v.z, v.w); }
+)CUDA";
+
+static void emit_fp_steps(std::ostringstream& o, const std::vector<b2z_circuit::Step>& steps, const b2z_circuit* c, bool trace_domain,
+                          std::vector<uint8_t>* is_ext_out) {
+  // emits the fp-valued steps; returns per-var ext flags
+  std::vector<uint8_t> is_ext;
+  size_t nf = 0;
+  auto nm = [&](size_t v) { return std::string(is_ext[v] ? "e" : "f") + std::to_string(v); };
+  for (const auto& s : steps) {
+    switch (s.op) {
+      case OP_CONST:
+        is_ext.push_back(0);
+        o << "  const u32 f" << nf << " = " << fp_from_u32(s.a) << "u;\n";
+        nf++;
+        break;
+      case OP_CONST_EXT:
+        is_ext.push_back(1);
+        o << "  const E e" << nf << " = emake(" << fp_from_u32(s.a) << "u, " << fp_from_u32(s.b) << "u, " << fp_from_u32(s.c) << "u, "
+          << fp_from_u32(s.d) << "u);\n";
+        nf++;
+        break;
+      case OP_GET: {
+        is_ext.push_back(0);
+        uint32_t g = c->tap_group[s.a], col = c->tap_offset[s.a], back = c->tap_back[s.a];
+        unsigned stride = trace_domain ? 1 : 4;
+        o << "  const u32 f" << nf << " = __ldg(g" << g << " + " << col << "ull * domain + ((i - " << (back * stride) << "ull) & mask));\n";
+        nf++;
+      } break;
+      case OP_GET_GLOBAL:
+        is_ext.push_back(0);
+        o << "  const u32 f" << nf << " = __ldg(" << (s.a == 0 ? "globals" : "mixg") << " + " << s.b << ");\n";
+        nf++;
+        break;
+      case OP_ADD: case OP_SUB: case OP_MUL: {
+        bool ea = is_ext[s.a], eb = is_ext[s.b];
+        is_ext.push_back(ea | eb);
+        std::string A = nm(s.a), Bn = nm(s.b);
+        std::string expr;
+        if (!ea && !eb) expr = std::string(s.op == OP_ADD ? "fadd" : s.op == OP_SUB ? "fsub" : "fmul") + "(" + A + ", " + Bn + ")";
+        else if (ea && eb) expr = std::string(s.op == OP_ADD ? "eadd" : s.op == OP_SUB ? "esub" : "emul") + "(" + A + ", " + Bn + ")";
+        else if (ea && !eb) expr = std::string(s.op == OP_ADD ? "eaddf" : s.op == OP_SUB ? "esubf" : "emulf") + "(" + A + ", " + Bn + ")";
+        else expr = s.op == OP_ADD ? "eaddf(" + Bn + ", " + A + ")" : s.op == OP_SUB ? "fsube(" + A + ", " + Bn + ")" : "emulf(" + Bn + ", " + A + ")";
+        o << "  const " << ((ea | eb) ? "E e" : "u32 f") << nf << " = " << expr << ";\n";
+        nf++;
+      } break;
+      default: break;
+    }
+  }
+  if (is_ext_out) *is_ext_out = is_ext;
+}
+
+void circuit_codegen(b2z_circuit* c) {
+  std::ostringstream o;
+  o << PRELUDE;
+  o << "// circuit \"" << std::string((const char*)c->info, 16) << "\": " << c->steps.size() << " constraint steps, " << c->n_taps
+    << " taps\n";
+  // ---- eval_check: one thread per point of the 4N coset ----
+  o << "extern \"C\" __global__ void __launch_bounds__(256) b2z_eval_check(u32* __restrict__ check, const u32* __restrict__ g0, "
+       "const u32* __restrict__ g1, const u32* __restrict__ g2, const u32* __restrict__ globals, const u32* __restrict__ mixg, "
+       "const u32* __restrict__ pm, u32 iz0, u32 iz1, u32 iz2, u32 iz3, u64 mask) {\n";
+  o << "  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;\n  if (i > mask) return;\n  const u64 domain = mask + 1;\n";
+  {
+    // interleave fp and mix steps in program order
+    std::vector<uint8_t> is_ext;
+    size_t nf = 0, nmx = 0;
+    auto nm = [&](size_t v) { return std::string(is_ext[v] ? "e" : "f") + std::to_string(v); };
+    for (const auto& s : c->steps) {
+      switch (s.op) {
+        case OP_TRUE:
+          o << "  const E m" << nmx << " = emake(0u, 0u, 0u, 0u);\n";
+          nmx++;
+          break;
+        case OP_AND_EQZ: {
+          std::string pw = "eld(pm + " + std::to_string(4 * c->mix_exp[s.a]) + ")";
+          std::string term = is_ext[s.b] ? "emul(" + pw + ", " + nm(s.b) + ")" : "emulf(" + pw + ", " + nm(s.b) + ")";
+          o << "  const E m" << nmx << " = eadd(m" << s.a << ", " << term << ");\n";
+          nmx++;
+        } break;
+        case OP_AND_COND: {
+          std::string pw = "eld(pm + " + std::to_string(4 * c->mix_exp[s.a]) + ")";
+          std::string inner = is_ext[s.b] ? "emul(m" + std::to_string(s.c) + ", " + nm(s.b) + ")" : "emulf(m" + std::to_string(s.c) + ", " + nm(s.b) + ")";
+          o << "  const E m" << nmx << " = eadd(m" << s.a << ", emul(" << inner << ", " << pw << "));\n";
+          nmx++;
+        } break;
+        default: {
+          std::vector<b2z_circuit::Step> one{s};
+          // emit a single fp step with correct numbering: reuse emit logic inline
+          switch (s.op) {
+            case OP_CONST:
+              is_ext.push_back(0);
+              o << "  const u32 f" << nf << " = " << fp_from_u32(s.a) << "u;\n";
+              break;
+            case OP_CONST_EXT:
+              is_ext.push_back(1);
+              o << "  const E e" << nf << " = emake(" << fp_from_u32(s.a) << "u, " << fp_from_u32(s.b) << "u, " << fp_from_u32(s.c)
+                << "u, " << fp_from_u32(s.d) << "u);\n";
+              break;
+            case OP_GET: {
+              is_ext.push_back(0);
+              uint32_t g = c->tap_group[s.a], col = c->tap_offset[s.a], back = c->tap_back[s.a];
+              o << "  const u32 f" << nf << " = __ldg(g" << g << " + " << col << "ull * domain + ((i - " << (back * 4) << "ull) & mask));\n";
+            } break;
+            case OP_GET_GLOBAL:
+              is_ext.push_back(0);
+              o << "  const u32 f" << nf << " = __ldg(" << (s.a == 0 ? "globals" : "mixg") << " + " << s.b << ");\n";
+              break;
+            default: {
+              bool ea = is_ext[s.a], eb = is_ext[s.b];
+              std::string A = nm(s.a), Bn = nm(s.b), expr;
+              if (!ea && !eb) expr = std::string(s.op == OP_ADD ? "fadd" : s.op == OP_SUB ? "fsub" : "fmul") + "(" + A + ", " + Bn + ")";
+              else if (ea && eb) expr = std::string(s.op == OP_ADD ? "eadd" : s.op == OP_SUB ? "esub" : "emul") + "(" + A + ", " + Bn + ")";
+              else if (ea && !eb) expr = std::string(s.op == OP_ADD ? "eaddf" : s.op == OP_SUB ? "esubf" : "emulf") + "(" + A + ", " + Bn + ")";
+              else expr = s.op == OP_ADD ? "eaddf(" + Bn + ", " + A + ")" : s.op == OP_SUB ? "fsube(" + A + ", " + Bn + ")" : "emulf(" + Bn + ", " + A + ")";
+              is_ext.push_back(ea | eb);
+              o << "  const " << ((ea | eb) ? "E e" : "u32 f") << nf << " = " << expr << ";\n";
+            } break;
+          }
+          nf++;
+        } break;
+      }
+    }
+  }
+  o << "  const u32 izs[4] = {iz0, iz1, iz2, iz3};\n";
+  o << "  const E r = emulf(m" << c->ret << ", izs[i & 3]);\n";
+  o << "  check[i] = r.a; check[domain + i] = r.b; check[2 * domain + i] = r.c; check[3 * domain + i] = r.d;\n}\n\n";
+  // ---- witgen: one thread per active trace row; taps read the trace domain (stride 1) ----
+  o << "extern \"C\" __global__ void __launch_bounds__(256) b2z_witgen(u32* __restrict__ g2w, const u32* __restrict__ g1, "
+       "const u32* __restrict__ globals, u64 mask, u64 active_rows) {\n";
+  o << "  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;\n  if (i >= active_rows) return;\n  const u64 domain = mask + 1;\n";
+  o << "  const u32* g2 = g2w; const u32* g0 = 0; const u32* mixg = 0; (void)g0; (void)mixg;\n";
+  std::vector<uint8_t> wext;
+  emit_fp_steps(o, c->wit_steps, c, true, &wext);
+  for (size_t k = 0; k < c->wit_store_col.size(); k++)
+    o << "  g2w[" << c->wit_store_col[k] << "ull * domain + i] = f" << c->wit_store_var[k] << ";\n";
+  o << "}\n";
+  c->source = o.str();
+  uint64_t h = 1469598103934665603ull;
+  for (unsigned char ch : c->source) {
+    h ^= ch;
+    h *= 1099511628211ull;
+  }
+  c->source_hash = h;
+}
+
+// ---------------- NVRTC (dlopen'd) + cubin cache ----------------
+typedef struct _nvrtcProgram* nvrtcProgram;
+struct Nvrtc {
+  void* h = nullptr;
+  int (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+  int (*CompileProgram)(nvrtcProgram, int, const char* const*) = nullptr;
+  int (*GetCUBINSize)(nvrtcProgram, size_t*) = nullptr;
+  int (*GetCUBIN)(nvrtcProgram, char*) = nullptr;
+  int (*GetProgramLogSize)(nvrtcProgram, size_t*) = nullptr;
+  int (*GetProgramLog)(nvrtcProgram, char*) = nullptr;
+  int (*DestroyProgram)(nvrtcProgram*) = nullptr;
+  bool load() {
+    if (h) return true;
+    const char* names[] = {"libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so", "libnvrtc.so"};
+    for (const char* nme : names) {
+      h = dlopen(nme, RTLD_NOW | RTLD_LOCAL);
+      if (h) break;
+    }
+    if (!h) return false;
+#define LOADSYM(field, name) *(void**)(&field) = dlsym(h, name); if (!field) return false;
+    LOADSYM(CreateProgram, "nvrtcCreateProgram")
+    LOADSYM(CompileProgram, "nvrtcCompileProgram")
+    LOADSYM(GetCUBINSize, "nvrtcGetCUBINSize")
+    LOADSYM(GetCUBIN, "nvrtcGetCUBIN")
+    LOADSYM(GetProgramLogSize, "nvrtcGetProgramLogSize")
+    LOADSYM(GetProgramLog, "nvrtcGetProgramLog")
+    LOADSYM(DestroyProgram, "nvrtcDestroyProgram")
+#undef LOADSYM
+    return true;
+  }
+};
+static Nvrtc g_nvrtc;
+
+static std::string cache_dir() {
+  if (const char* e = getenv("B2Z_KERNEL_CACHE")) return e;
+  Dl_info info;
+  if (dladdr((void*)&circuit_codegen, &info) && info.dli_fname) {
+    std::string p = info.dli_fname;
+    size_t slash = p.rfind('/');
+    std::string dir = (slash == std::string::npos ? std::string(".") : p.substr(0, slash)) + "/kernel_cache";
+    return dir;
+  }
+  return "./kernel_cache";
+}
+
+b2z_err circuit_cubin(b2z_circuit* c, std::vector<char>& cubin) {
+  char name[64];
+  snprintf(name, sizeof name, "/circuit_%016llx.cubin", (unsigned long long)c->source_hash);
+  std::string dir = cache_dir(), path = dir + name;
+  {
+    std::ifstream f(path, std::ios::binary);
+    if (f) {
+      cubin.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
+      if (!cubin.empty()) return nullptr;
+    }
+  }
+  B2Z_REQUIRE(g_nvrtc.load(), "circuit kernels are not in the cubin cache and libnvrtc.so.12 could not be loaded");
+  nvrtcProgram prog = nullptr;
+  int rc = g_nvrtc.CreateProgram(&prog, c->source.c_str(), "b2z_circuit.cu", 0, nullptr, nullptr);
+  B2Z_REQUIRE(rc == 0, "nvrtcCreateProgram failed");
+  const char* opts[] = {"--gpu-architecture=sm_100a", "-lineinfo", "--std=c++17"};
+  rc = g_nvrtc.CompileProgram(prog, 3, opts);
+  if (rc != 0) {
+    size_t ls = 0;
+    g_nvrtc.GetProgramLogSize(prog, &ls);
+    std::string log(ls, '\0');
+    if (ls) g_nvrtc.GetProgramLog(prog, &log[0]);
+    g_nvrtc.DestroyProgram(&prog);
+    return set_error("NVRTC compile failed: " + log.substr(0, 2000));
+  }
+  size_t sz = 0;
+  g_nvrtc.GetCUBINSize(prog, &sz);
+  cubin.resize(sz);
+  g_nvrtc.GetCUBIN(prog, cubin.data());
+  g_nvrtc.DestroyProgram(&prog);
+  mkdir(dir.c_str(), 0755);
+  std::ofstream f(path + ".tmp", std::ios::binary);
+  if (f) {
+    f.write(cubin.data(), (std::streamsize)cubin.size());
+    f.close();
+    rename((path + ".tmp").c_str(), path.c_str());
+  }
+  return nullptr;
+}
+
+b2z_err circuit_compile(b2z_ctx* ctx, b2z_circuit* c) {
+  std::vector<char> cubin;
+  B2Z_TRY(circuit_cubin(c, cubin));
+  B2Z_CUDA(cudaLibraryLoadData(&c->library, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+  B2Z_CUDA(cudaLibraryGetKernel(&c->k_eval_check, c->library, "b2z_eval_check"));
+  B2Z_CUDA(cudaLibraryGetKernel(&c->k_witgen, c->library, "b2z_witgen"));
+  c->device = ctx->device;
+  if (!c->accum_col.empty()) {
+    B2Z_CUDA(cudaMalloc(&c->accum_col_dev, 4 * c->accum_col.size()));
+    B2Z_CUDA(cudaMemcpy(c->accum_col_dev, c->accum_col.data(), 4 * c->accum_col.size(), cudaMemcpyHostToDevice));
+  }
+  if (!c->col_kind.empty()) {
+    B2Z_CUDA(cudaMalloc(&c->col_kind_dev, c->col_kind.size()));
+    B2Z_CUDA(cudaMemcpy(c->col_kind_dev, c->col_kind.data(), c->col_kind.size(), cudaMemcpyHostToDevice));
+  }
+  return nullptr;
+}
+
+}  // namespace b2z

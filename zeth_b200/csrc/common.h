@@ -1,0 +1,104 @@
+// Shared host-side declarations of the product library (context, error plumbing, kernel launch entry points).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/b2z.h"
+#include "field.cuh"
+
+namespace b2z {
+
+// thread-local error slot: entry points return its c_str() (upstream FFI convention: NULL == success)
+const char* set_error(const std::string& msg);
+
+#define B2Z_CUDA(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess)                                                                          \
+      return ::b2z::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                  \
+  } while (0)
+#define B2Z_TRY(expr)                  \
+  do {                                 \
+    const char* _err = (expr);         \
+    if (_err) return _err;             \
+  } while (0)
+#define B2Z_REQUIRE(cond, msg)                       \
+  do {                                               \
+    if (!(cond)) return ::b2z::set_error(msg);       \
+  } while (0)
+
+constexpr int MAX_PO2 = 26;  // largest transform: po2 24 trace x 4 (INV_RATE)
+
+}  // namespace b2z
+
+struct b2z_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  uint64_t launches = 0;
+  // per-size device tables, built lazily: forward / inverse twiddles w_n^k (k < n/2), 3^rev(j) for zk_shift
+  uint32_t* tw_fwd[b2z::MAX_PO2 + 1] = {};
+  uint32_t* tw_rev[b2z::MAX_PO2 + 1] = {};
+  uint32_t* pow3rev[b2z::MAX_PO2 + 1] = {};
+  // pinned staging for small transcript round trips
+  uint32_t* pinned = nullptr;
+  size_t pinned_words = 0;
+  // phase timing of the last prove call
+  std::vector<double> phase_ms;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> phase_events;
+};
+
+namespace b2z {
+
+// ---- kernel launchers (kernels_*.cu); all enqueue on ctx->stream and bump ctx->launches ----
+b2z_err ensure_tables(b2z_ctx* ctx, unsigned po2, bool fwd, bool rev, bool pow3);
+b2z_err launch_interpolate(b2z_ctx* ctx, uint32_t* io, size_t count, unsigned po2, bool fuse_zk_shift);
+b2z_err launch_evaluate(b2z_ctx* ctx, uint32_t* out, const uint32_t* in, size_t count, unsigned out_po2, unsigned expand_bits);
+b2z_err launch_bit_reverse(b2z_ctx* ctx, uint32_t* io, size_t count, unsigned po2);
+b2z_err launch_zk_shift(b2z_ctx* ctx, uint32_t* io, size_t count, unsigned po2);
+b2z_err launch_hash_rows(b2z_ctx* ctx, uint32_t* out, const uint32_t* matrix, size_t rows, size_t cols);
+b2z_err launch_hash_fold(b2z_ctx* ctx, uint32_t* nodes, size_t in_size, size_t out_size);
+b2z_err launch_fri_fold(b2z_ctx* ctx, uint32_t* out, const uint32_t* in, const Fp4& mix, size_t out_count);
+b2z_err launch_evaluate_any(b2z_ctx* ctx, const uint32_t* coeffs, unsigned po2, const uint32_t* which, const uint32_t* xs,
+                            size_t eval_count, uint32_t* out);
+b2z_err launch_mix_poly_coeffs(b2z_ctx* ctx, uint32_t* out, const Fp4& mix_start, const Fp4& mix, const uint32_t* in,
+                               const uint32_t* combos_dev, size_t input_size, size_t count);
+b2z_err launch_add_elem(b2z_ctx* ctx, uint32_t* out, const uint32_t* a, const uint32_t* b, size_t n);
+b2z_err launch_sum_extelem(b2z_ctx* ctx, uint32_t* out, const uint32_t* in, size_t count, size_t to_add);
+b2z_err launch_zeroize(b2z_ctx* ctx, uint32_t* io, size_t n);
+b2z_err launch_gather_sample(b2z_ctx* ctx, uint32_t* dst, const uint32_t* src, size_t idx, size_t size, size_t stride);
+b2z_err launch_poly_divide(b2z_ctx* ctx, uint32_t* ext_coeffs, size_t count, const Fp4& z, uint32_t* remainder_dev);
+b2z_err launch_sub_lowcoeffs(b2z_ctx* ctx, uint32_t* ext_coeffs, const uint32_t* sub_dev, size_t n_sub);
+b2z_err launch_accum(b2z_ctx* ctx, uint32_t* accum, const uint32_t* data, const uint32_t* accum_cols_dev, size_t n_accum,
+                     const uint32_t* mix_dev, const uint32_t* noise_dev, unsigned po2, size_t zk_rows);
+// query gathering: writes rows + Merkle paths for all queries straight into the device seal image
+struct GatherTree {
+  const uint32_t* matrix;
+  const uint32_t* nodes;
+  uint32_t rows, cols, top_size;
+  uint32_t seal_off;  // word offset of this tree's section inside one query record
+  uint32_t shift;     // query position -> row: idx = pos & (rows-1) for FRI rounds (pos % rows)
+};
+b2z_err launch_gather_queries(b2z_ctx* ctx, uint32_t* seal_dev, const GatherTree* trees_dev, size_t n_trees,
+                              const uint32_t* positions_dev, size_t n_queries, size_t record_words);
+
+// host Poseidon2 / transcript (transcript.cpp)
+void host_poseidon2_mix(uint32_t* state24);
+void host_hash_elem_slice(const uint32_t* in, size_t n, uint32_t* digest);
+void host_hash_pair(const uint32_t* a, const uint32_t* b, uint32_t* digest);
+struct HostRng {
+  uint32_t cells[24] = {};
+  unsigned pool_used = 0;
+  void mix(const uint32_t* digest);
+  uint32_t random_elem();
+  Fp4 random_ext();
+  uint32_t random_bits(unsigned bits);
+};
+
+}  // namespace b2z

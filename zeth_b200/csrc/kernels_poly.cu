@@ -1,0 +1,470 @@
+// Polynomial / element-wise kernels of the segment prover: fri_fold, batch_evaluate_any, mix_poly_coeffs,
+// eltwise_*, gather_sample, DEEP synthetic division, accumulate, and the batched query gather.
+//
+// Semantics: risc0-zkp 3.0.2 hal/cpu.rs (fri_fold, batch_evaluate_any, mix_poly_coeffs, eltwise_*, gather_sample),
+// core/poly.rs poly_divide and prove/merkle.rs MerkleTreeProver::prove (rows a13-a16).
+// All of these are HBM-bandwidth bound: one coalesced read of the inputs, ext-field arithmetic in registers.
+#include "common.h"
+
+namespace b2z {
+
+// ---------------- fri_fold ----------------
+// out[k][idx] = sum_{i<16} mix^i * in[k'][rev4(i)*count + idx]  on component-major [4][.] buffers
+__global__ void fri_fold_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ in, Fp4 mix, size_t count) {
+  size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (idx >= count) return;
+  size_t in_count = count * 16;
+  Fp4 tot = fp4_zero(), cur = fp4_one();
+#pragma unroll
+  for (unsigned i = 0; i < 16; i++) {
+    size_t ri = (size_t)bit_rev(i, 4) * count + idx;
+    Fp4 f = fp4_make(__ldg(in + ri), __ldg(in + in_count + ri), __ldg(in + 2 * in_count + ri), __ldg(in + 3 * in_count + ri));
+    tot = fp4_add(tot, fp4_mul(cur, f));
+    cur = fp4_mul(cur, mix);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) out[k * count + idx] = tot.e[k];
+}
+b2z_err launch_fri_fold(b2z_ctx* ctx, uint32_t* out, const uint32_t* in, const Fp4& mix, size_t count) {
+  if (!count) return nullptr;
+  fri_fold_kernel<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(out, in, mix, count);
+  ctx->launches++;
+  B2Z_CUDA(cudaGetLastError());
+  return nullptr;
+}
+
+// ---------------- batch_evaluate_any ----------------
+// out[i] = sum_j coeffs[which[i]][j] * xs[i]^j.  Grid (chunks, evals): thread t of a chunk owns coefficients
+// j = chunk_base + t + k*T (coalesced), runs Horner in x^T, then scales by x^(chunk_base + t); block tree-reduces;
+// partial sums are combined with one atomic-free second kernel.
+constexpr unsigned EA_THREADS = 256;
+constexpr unsigned EA_PER_THREAD = 16;
+__global__ void __launch_bounds__(EA_THREADS) evaluate_any_kernel(const uint32_t* __restrict__ coeffs, unsigned po2,
+                                                                  const uint32_t* __restrict__ which, const uint32_t* __restrict__ xs,
+                                                                  uint32_t* __restrict__ partial, unsigned chunks) {
+  __shared__ Fp4 red[EA_THREADS];
+  const size_t n = (size_t)1 << po2;
+  const unsigned ev = blockIdx.y, chunk = blockIdx.x, t = threadIdx.x;
+  const uint32_t* p = coeffs + (size_t)which[ev] * n;
+  Fp4 x = fp4_make(xs[4 * ev], xs[4 * ev + 1], xs[4 * ev + 2], xs[4 * ev + 3]);
+  const size_t chunk_elems = (size_t)EA_THREADS * EA_PER_THREAD;
+  const size_t base = chunk * chunk_elems;
+  Fp4 xT = fp4_pow(x, EA_THREADS);
+  Fp4 acc = fp4_zero();
+#pragma unroll
+  for (int k = EA_PER_THREAD - 1; k >= 0; k--) {
+    size_t j = base + t + (size_t)k * EA_THREADS;
+    uint32_t c = j < n ? __ldg(p + j) : 0u;
+    acc = fp4_add_fp(fp4_mul(acc, xT), c);
+  }
+  acc = fp4_mul(acc, fp4_pow(x, base + t));
+  red[t] = acc;
+  __syncthreads();
+  for (unsigned s = EA_THREADS / 2; s > 0; s >>= 1) {
+    if (t < s) red[t] = fp4_add(red[t], red[t + s]);
+    __syncthreads();
+  }
+  if (t == 0) {
+    uint32_t* o = partial + 4 * ((size_t)ev * chunks + chunk);
+    o[0] = red[0].e[0]; o[1] = red[0].e[1]; o[2] = red[0].e[2]; o[3] = red[0].e[3];
+  }
+}
+__global__ void evaluate_any_reduce_kernel(const uint32_t* __restrict__ partial, uint32_t* __restrict__ out, unsigned chunks,
+                                           size_t evals) {
+  size_t ev = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (ev >= evals) return;
+  Fp4 tot = fp4_zero();
+  for (unsigned c = 0; c < chunks; c++) {
+    const uint32_t* q = partial + 4 * (ev * chunks + c);
+    tot = fp4_add(tot, fp4_make(q[0], q[1], q[2], q[3]));
+  }
+  out[4 * ev] = tot.e[0]; out[4 * ev + 1] = tot.e[1]; out[4 * ev + 2] = tot.e[2]; out[4 * ev + 3] = tot.e[3];
+}
+b2z_err launch_evaluate_any(b2z_ctx* ctx, const uint32_t* coeffs, unsigned po2, const uint32_t* which, const uint32_t* xs,
+                            size_t eval_count, uint32_t* out) {
+  if (!eval_count) return nullptr;
+  size_t n = (size_t)1 << po2;
+  size_t chunk_elems = (size_t)EA_THREADS * EA_PER_THREAD;
+  unsigned chunks = (unsigned)((n + chunk_elems - 1) / chunk_elems);
+  B2Z_REQUIRE(eval_count <= 65535, "too many evaluation points for one launch");
+  uint32_t* partial = nullptr;
+  B2Z_CUDA(cudaMallocAsync(&partial, sizeof(uint32_t) * 4 * eval_count * chunks, ctx->stream));
+  evaluate_any_kernel<<<dim3(chunks, (unsigned)eval_count), EA_THREADS, 0, ctx->stream>>>(coeffs, po2, which, xs, partial, chunks);
+  evaluate_any_reduce_kernel<<<(unsigned)((eval_count + 127) / 128), 128, 0, ctx->stream>>>(partial, out, chunks, eval_count);
+  ctx->launches += 2;
+  B2Z_CUDA(cudaGetLastError());
+  B2Z_CUDA(cudaFreeAsync(partial, ctx->stream));
+  return nullptr;
+}
+
+// ---------------- mix_poly_coeffs ----------------
+// out[combos[i]][idx] += mix_start * mix^i * in[i][idx]   (out: AoS ext [n_combos+1][count])
+// Up to MPC_MAX_COMBOS accumulators stay in registers; powers of mix come from a device table.
+constexpr int MPC_MAX_COMBOS = 8;
+__global__ void mix_pow_table_kernel(uint32_t* tab, Fp4 start, Fp4 mix, size_t n) {
+  // tab[i] = start * mix^i ; one thread per 64 entries (pow for the first, then running product)
+  size_t b = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) * 64;
+  if (b >= n) return;
+  Fp4 cur = fp4_mul(start, fp4_pow(mix, b));
+  for (size_t i = b; i < b + 64 && i < n; i++) {
+    tab[4 * i] = cur.e[0]; tab[4 * i + 1] = cur.e[1]; tab[4 * i + 2] = cur.e[2]; tab[4 * i + 3] = cur.e[3];
+    cur = fp4_mul(cur, mix);
+  }
+}
+__global__ void __launch_bounds__(256) mix_poly_coeffs_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ pows,
+                                                              const uint32_t* __restrict__ in, const uint32_t* __restrict__ combos,
+                                                              size_t input_size, size_t count, unsigned combo_lo, unsigned combo_hi) {
+  size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (idx >= count) return;
+  Fp4 acc[MPC_MAX_COMBOS];
+#pragma unroll
+  for (int k = 0; k < MPC_MAX_COMBOS; k++) acc[k] = fp4_zero();
+  for (size_t i = 0; i < input_size; i++) {
+    unsigned cid = combos[i];
+    if (cid < combo_lo || cid >= combo_hi) continue;
+    uint32_t v = __ldg(in + i * count + idx);
+    const uint4 pw = *reinterpret_cast<const uint4*>(pows + 4 * i);
+    Fp4 term = fp4_make(fp_mul(pw.x, v), fp_mul(pw.y, v), fp_mul(pw.z, v), fp_mul(pw.w, v));
+    unsigned slot = cid - combo_lo;
+#pragma unroll
+    for (int k = 0; k < MPC_MAX_COMBOS; k++)
+      if ((unsigned)k == slot) acc[k] = fp4_add(acc[k], term);
+  }
+#pragma unroll
+  for (int k = 0; k < MPC_MAX_COMBOS; k++) {
+    if (combo_lo + k >= combo_hi) break;
+    uint4* o = reinterpret_cast<uint4*>(out + 4 * ((size_t)(combo_lo + k) * count + idx));
+    uint4 cur = *o;
+    Fp4 r = fp4_add(fp4_make(cur.x, cur.y, cur.z, cur.w), acc[k]);
+    *o = make_uint4(r.e[0], r.e[1], r.e[2], r.e[3]);
+  }
+}
+b2z_err launch_mix_poly_coeffs(b2z_ctx* ctx, uint32_t* out, const Fp4& mix_start, const Fp4& mix, const uint32_t* in,
+                               const uint32_t* combos_dev, size_t input_size, size_t count) {
+  if (!input_size || !count) return nullptr;
+  // combo id range (host needs it to size the register accumulators): fetch the ids (small) synchronously
+  std::vector<uint32_t> ids(input_size);
+  B2Z_CUDA(cudaMemcpyAsync(ids.data(), combos_dev, 4 * input_size, cudaMemcpyDeviceToHost, ctx->stream));
+  B2Z_CUDA(cudaStreamSynchronize(ctx->stream));
+  uint32_t lo = ids[0], hi = ids[0];
+  for (uint32_t v : ids) { lo = v < lo ? v : lo; hi = v > hi ? v : hi; }
+  uint32_t* pows = nullptr;
+  B2Z_CUDA(cudaMallocAsync(&pows, 16 * input_size, ctx->stream));
+  size_t tthreads = (input_size + 63) / 64;
+  mix_pow_table_kernel<<<(unsigned)((tthreads + 63) / 64), 64, 0, ctx->stream>>>(pows, mix_start, mix, input_size);
+  ctx->launches++;
+  for (uint32_t c0 = lo; c0 <= hi; c0 += MPC_MAX_COMBOS) {
+    uint32_t c1 = c0 + MPC_MAX_COMBOS < hi + 1 ? c0 + MPC_MAX_COMBOS : hi + 1;
+    mix_poly_coeffs_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(out, pows, in, combos_dev, input_size, count, c0, c1);
+    ctx->launches++;
+  }
+  B2Z_CUDA(cudaGetLastError());
+  B2Z_CUDA(cudaFreeAsync(pows, ctx->stream));
+  return nullptr;
+}
+
+// ---------------- element-wise ----------------
+__global__ void add_elem_kernel(uint32_t* out, const uint32_t* a, const uint32_t* b, size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = fp_add(a[i], b[i]);
+}
+b2z_err launch_add_elem(b2z_ctx* ctx, uint32_t* out, const uint32_t* a, const uint32_t* b, size_t n) {
+  if (!n) return nullptr;
+  add_elem_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(out, a, b, n);
+  ctx->launches++;
+  B2Z_CUDA(cudaGetLastError());
+  return nullptr;
+}
+// AoS ext input [to_add][count] -> component-major [4][count]
+__global__ void sum_extelem_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ in, size_t count, size_t to_add) {
+  size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (idx >= count) return;
+  Fp4 tot = fp4_zero();
+  for (size_t i = 0; i < to_add; i++) {
+    uint4 v = *reinterpret_cast<const uint4*>(in + 4 * (i * count + idx));
+    tot = fp4_add(tot, fp4_make(v.x, v.y, v.z, v.w));
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) out[k * count + idx] = tot.e[k];
+}
+b2z_err launch_sum_extelem(b2z_ctx* ctx, uint32_t* out, const uint32_t* in, size_t count, size_t to_add) {
+  if (!count) return nullptr;
+  sum_extelem_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(out, in, count, to_add);
+  ctx->launches++;
+  B2Z_CUDA(cudaGetLastError());
+  return nullptr;
+}
+__global__ void zeroize_kernel(uint32_t* io, size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n && io[i] == INVALID) io[i] = 0;
+}
+b2z_err launch_zeroize(b2z_ctx* ctx, uint32_t* io, size_t n) {
+  if (!n) return nullptr;
+  zeroize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(io, n);
+  ctx->launches++;
+  B2Z_CUDA(cudaGetLastError());
+  return nullptr;
+}
+__global__ void gather_sample_kernel(uint32_t* dst, const uint32_t* src, size_t idx, size_t size, size_t stride) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < size) dst[i] = src[idx + i * stride];
+}
+b2z_err launch_gather_sample(b2z_ctx* ctx, uint32_t* dst, const uint32_t* src, size_t idx, size_t size, size_t stride) {
+  if (!size) return nullptr;
+  gather_sample_kernel<<<(unsigned)((size + 255) / 256), 256, 0, ctx->stream>>>(dst, src, idx, size, stride);
+  ctx->launches++;
+  B2Z_CUDA(cudaGetLastError());
+  return nullptr;
+}
+
+// ---------------- DEEP synthetic division ----------------
+// In-place division of the ext polynomial p (count AoS coefficients, natural order) by (X - z):
+//   q[i] = sum_{j>i} p[j] z^(j-i-1)   (core/poly.rs poly_divide), remainder = sum_j p[j] z^j.
+// Parallel form: segment s of L coefficients computes S_s = sum_{j in seg} p[j] z^(j - start_s) (Horner); the
+// carry into segment s is C_s = sum_{s'>s} S_s' z^(L (s'-s-1)), a suffix scan with multiplier z^L done in two
+// levels (within a block through shared memory, across blocks by a single-block kernel).
+constexpr unsigned PD_L = 8;         // coefficients per thread
+constexpr unsigned PD_THREADS = 256; // segments per block
+__device__ __forceinline__ Fp4 ld_ext(const uint32_t* p) {
+  uint4 v = *reinterpret_cast<const uint4*>(p);
+  return fp4_make(v.x, v.y, v.z, v.w);
+}
+__device__ __forceinline__ void st_ext(uint32_t* p, const Fp4& v) { *reinterpret_cast<uint4*>(p) = make_uint4(v.e[0], v.e[1], v.e[2], v.e[3]); }
+
+// suffix scan inside a block: on return sh[t] = sum_{t' >= t} S_t' zL^(t'-t)
+__device__ __forceinline__ void block_suffix_scan(Fp4* sh, Fp4 zL, unsigned t, unsigned nthreads) {
+  Fp4 mult = zL;
+  for (unsigned d = 1; d < nthreads; d <<= 1) {
+    Fp4 add = fp4_zero();
+    if (t + d < nthreads) add = fp4_mul(sh[t + d], mult);
+    __syncthreads();
+    sh[t] = fp4_add(sh[t], add);
+    __syncthreads();
+    mult = fp4_mul(mult, mult);
+  }
+}
+__global__ void __launch_bounds__(PD_THREADS) poly_divide_local_kernel(const uint32_t* __restrict__ p, size_t count, Fp4 z,
+                                                                       uint32_t* __restrict__ block_sums) {
+  __shared__ Fp4 sh[PD_THREADS];
+  unsigned t = threadIdx.x;
+  size_t start = ((size_t)blockIdx.x * PD_THREADS + t) * PD_L;
+  Fp4 acc = fp4_zero();
+#pragma unroll
+  for (int k = PD_L - 1; k >= 0; k--) {
+    size_t j = start + k;
+    Fp4 c = j < count ? ld_ext(p + 4 * j) : fp4_zero();
+    acc = fp4_add(fp4_mul(acc, z), c);
+  }
+  sh[t] = acc;
+  __syncthreads();
+  block_suffix_scan(sh, fp4_pow(z, PD_L), t, PD_THREADS);
+  if (t == 0) st_ext(block_sums + 4 * (size_t)blockIdx.x, sh[0]);
+}
+// single block: carry[b] = sum_{b' > b} blocksum[b'] * zB^(b'-b-1), zB = z^(L*THREADS); remainder = carry[-1]
+__global__ void poly_divide_carry_kernel(const uint32_t* __restrict__ block_sums, uint32_t* __restrict__ carries, size_t nblocks, Fp4 zB,
+                                         uint32_t* __restrict__ remainder) {
+  if (threadIdx.x != 0) return;
+  Fp4 cur = fp4_zero();
+  for (size_t b = nblocks; b-- > 0;) {
+    st_ext(carries + 4 * b, cur);
+    cur = fp4_add(fp4_mul(cur, zB), ld_ext(block_sums + 4 * b));
+  }
+  st_ext(remainder, cur);
+}
+__global__ void __launch_bounds__(PD_THREADS) poly_divide_apply_kernel(uint32_t* __restrict__ p, size_t count, Fp4 z,
+                                                                       const uint32_t* __restrict__ carries) {
+  __shared__ Fp4 sh[PD_THREADS + 1];
+  unsigned t = threadIdx.x;
+  size_t start = ((size_t)blockIdx.x * PD_THREADS + t) * PD_L;
+  Fp4 c[PD_L];
+  Fp4 acc = fp4_zero();
+#pragma unroll
+  for (int k = PD_L - 1; k >= 0; k--) {
+    size_t j = start + k;
+    c[k] = j < count ? ld_ext(p + 4 * j) : fp4_zero();
+    acc = fp4_add(fp4_mul(acc, z), c[k]);
+  }
+  sh[t] = acc;
+  if (t == 0) sh[PD_THREADS] = fp4_zero();
+  __syncthreads();
+  Fp4 zL = fp4_pow(z, PD_L);
+  block_suffix_scan(sh, zL, t, PD_THREADS);
+  // carry into this thread's segment = (suffix of later segments in block) + block carry * zL^(segments after t)
+  Fp4 later = (t + 1 < PD_THREADS) ? sh[t + 1] : fp4_zero();
+  Fp4 bc = ld_ext(carries + 4 * (size_t)blockIdx.x);
+  Fp4 cur = fp4_add(later, fp4_mul(bc, fp4_pow(zL, PD_THREADS - 1 - t)));
+  // walk the segment downwards: q[j] = cur ; cur = cur*z + p[j]
+#pragma unroll
+  for (int k = PD_L - 1; k >= 0; k--) {
+    size_t j = start + k;
+    if (j < count) st_ext(p + 4 * j, cur);
+    cur = fp4_add(fp4_mul(cur, z), c[k]);
+  }
+}
+b2z_err launch_poly_divide(b2z_ctx* ctx, uint32_t* ext_coeffs, size_t count, const Fp4& z, uint32_t* remainder_dev) {
+  if (!count) return nullptr;
+  size_t per_block = (size_t)PD_L * PD_THREADS;
+  size_t nblocks = (count + per_block - 1) / per_block;
+  uint32_t* tmp = nullptr;
+  B2Z_CUDA(cudaMallocAsync(&tmp, 16 * 2 * nblocks, ctx->stream));
+  uint32_t* sums = tmp;
+  uint32_t* carries = tmp + 4 * nblocks;
+  poly_divide_local_kernel<<<(unsigned)nblocks, PD_THREADS, 0, ctx->stream>>>(ext_coeffs, count, z, sums);
+  poly_divide_carry_kernel<<<1, 32, 0, ctx->stream>>>(sums, carries, nblocks, fp4_pow(z, per_block), remainder_dev);
+  poly_divide_apply_kernel<<<(unsigned)nblocks, PD_THREADS, 0, ctx->stream>>>(ext_coeffs, count, z, carries);
+  ctx->launches += 3;
+  B2Z_CUDA(cudaGetLastError());
+  B2Z_CUDA(cudaFreeAsync(tmp, ctx->stream));
+  return nullptr;
+}
+// p[i] -= sub[i] for the first n_sub ext coefficients (the interpolated U polynomial of a combo)
+__global__ void sub_lowcoeffs_kernel(uint32_t* p, const uint32_t* sub, size_t n_sub) {
+  size_t i = threadIdx.x;
+  if (i < n_sub) st_ext(p + 4 * i, fp4_sub(ld_ext(p + 4 * i), ld_ext(sub + 4 * i)));
+}
+b2z_err launch_sub_lowcoeffs(b2z_ctx* ctx, uint32_t* ext_coeffs, const uint32_t* sub_dev, size_t n_sub) {
+  if (!n_sub) return nullptr;
+  B2Z_REQUIRE(n_sub <= 32, "U polynomial too long");
+  sub_lowcoeffs_kernel<<<1, 32, 0, ctx->stream>>>(ext_coeffs, sub_dev, n_sub);
+  ctx->launches++;
+  B2Z_CUDA(cudaGetLastError());
+  return nullptr;
+}
+
+// ---------------- accumulate (synthetic circuits) ----------------
+// accumulator k: ext running sum over the active rows of 1 / (M_k + data[col_k][r]); noise in the last zk_rows rows.
+// Stage 1: per-row inverse terms (ext) written to the accum columns; stage 2: per-accumulator inclusive scan.
+__global__ void accum_terms_kernel(uint32_t* __restrict__ accum, const uint32_t* __restrict__ data, const uint32_t* __restrict__ cols,
+                                   const uint32_t* __restrict__ mix, const uint32_t* __restrict__ noise, unsigned po2, size_t zk_rows) {
+  size_t n = (size_t)1 << po2, active = n - zk_rows;
+  size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t k = blockIdx.y;
+  if (r >= n) return;
+  uint32_t* a = accum + 4 * k * n;
+  if (r >= active) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) a[j * n + r] = noise[(4 * k + j) * zk_rows + (r - active)];
+    return;
+  }
+  Fp4 m = fp4_make(mix[4 * k], mix[4 * k + 1], mix[4 * k + 2], mix[4 * k + 3]);
+  Fp4 t = fp4_inv(fp4_add_fp(m, __ldg(data + (size_t)cols[k] * n + r)));
+#pragma unroll
+  for (int j = 0; j < 4; j++) a[j * n + r] = t.e[j];
+}
+constexpr unsigned SCAN_THREADS = 256;
+constexpr unsigned SCAN_PER_THREAD = 16;
+// level 1: block-local inclusive scan of ext terms over [0, active); block totals out
+__global__ void __launch_bounds__(SCAN_THREADS) accum_scan_local_kernel(uint32_t* __restrict__ accum, unsigned po2, size_t active,
+                                                                        uint32_t* __restrict__ block_tot, size_t nblocks) {
+  __shared__ Fp4 sh[SCAN_THREADS];
+  size_t n = (size_t)1 << po2;
+  size_t k = blockIdx.y;
+  uint32_t* a = accum + 4 * k * n;
+  unsigned t = threadIdx.x;
+  size_t start = ((size_t)blockIdx.x * SCAN_THREADS + t) * SCAN_PER_THREAD;
+  Fp4 v[SCAN_PER_THREAD];
+  Fp4 run = fp4_zero();
+#pragma unroll
+  for (unsigned i = 0; i < SCAN_PER_THREAD; i++) {
+    size_t r = start + i;
+    v[i] = r < active ? fp4_make(a[r], a[n + r], a[2 * n + r], a[3 * n + r]) : fp4_zero();
+    run = fp4_add(run, v[i]);
+    v[i] = run;
+  }
+  sh[t] = run;
+  __syncthreads();
+  for (unsigned d = 1; d < SCAN_THREADS; d <<= 1) {
+    Fp4 add = fp4_zero();
+    if (t >= d) add = sh[t - d];
+    __syncthreads();
+    sh[t] = fp4_add(sh[t], add);
+    __syncthreads();
+  }
+  Fp4 prefix = t ? sh[t - 1] : fp4_zero();
+#pragma unroll
+  for (unsigned i = 0; i < SCAN_PER_THREAD; i++) {
+    size_t r = start + i;
+    if (r < active) {
+      Fp4 o = fp4_add(prefix, v[i]);
+      a[r] = o.e[0]; a[n + r] = o.e[1]; a[2 * n + r] = o.e[2]; a[3 * n + r] = o.e[3];
+    }
+  }
+  if (t == SCAN_THREADS - 1) st_ext(block_tot + 4 * (k * nblocks + blockIdx.x), sh[t]);
+}
+__global__ void accum_scan_carry_kernel(uint32_t* __restrict__ block_tot, size_t nblocks) {
+  // one thread per accumulator: exclusive scan of block totals in place
+  size_t k = blockIdx.x;
+  if (threadIdx.x != 0) return;
+  Fp4 run = fp4_zero();
+  for (size_t b = 0; b < nblocks; b++) {
+    Fp4 v = ld_ext(block_tot + 4 * (k * nblocks + b));
+    st_ext(block_tot + 4 * (k * nblocks + b), run);
+    run = fp4_add(run, v);
+  }
+}
+__global__ void __launch_bounds__(SCAN_THREADS) accum_scan_apply_kernel(uint32_t* __restrict__ accum, unsigned po2, size_t active,
+                                                                        const uint32_t* __restrict__ block_tot, size_t nblocks) {
+  size_t n = (size_t)1 << po2;
+  size_t k = blockIdx.y;
+  uint32_t* a = accum + 4 * k * n;
+  Fp4 carry = ld_ext(block_tot + 4 * (k * nblocks + blockIdx.x));
+  size_t base = (size_t)blockIdx.x * SCAN_THREADS * SCAN_PER_THREAD;
+  for (unsigned i = threadIdx.x; i < SCAN_THREADS * SCAN_PER_THREAD; i += SCAN_THREADS) {
+    size_t r = base + i;
+    if (r < active) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) a[j * n + r] = fp_add(a[j * n + r], carry.e[j]);
+    }
+  }
+}
+b2z_err launch_accum(b2z_ctx* ctx, uint32_t* accum, const uint32_t* data, const uint32_t* accum_cols_dev, size_t n_accum,
+                     const uint32_t* mix_dev, const uint32_t* noise_dev, unsigned po2, size_t zk_rows) {
+  if (!n_accum) return nullptr;
+  size_t n = (size_t)1 << po2, active = n - zk_rows;
+  accum_terms_kernel<<<dim3((unsigned)((n + 127) / 128), (unsigned)n_accum), 128, 0, ctx->stream>>>(accum, data, accum_cols_dev, mix_dev,
+                                                                                                    noise_dev, po2, zk_rows);
+  ctx->launches++;
+  size_t per_block = (size_t)SCAN_THREADS * SCAN_PER_THREAD;
+  size_t nblocks = (active + per_block - 1) / per_block;
+  if (nblocks == 0) return nullptr;
+  uint32_t* tot = nullptr;
+  B2Z_CUDA(cudaMallocAsync(&tot, 16 * n_accum * nblocks, ctx->stream));
+  accum_scan_local_kernel<<<dim3((unsigned)nblocks, (unsigned)n_accum), SCAN_THREADS, 0, ctx->stream>>>(accum, po2, active, tot, nblocks);
+  accum_scan_carry_kernel<<<(unsigned)n_accum, 32, 0, ctx->stream>>>(tot, nblocks);
+  accum_scan_apply_kernel<<<dim3((unsigned)nblocks, (unsigned)n_accum), SCAN_THREADS, 0, ctx->stream>>>(accum, po2, active, tot, nblocks);
+  ctx->launches += 3;
+  B2Z_CUDA(cudaGetLastError());
+  B2Z_CUDA(cudaFreeAsync(tot, ctx->stream));
+  return nullptr;
+}
+
+// ---------------- batched query gather ----------------
+// For query q and tree t: write row `idx` (cols words, gathered from the column-major matrix) followed by the sibling
+// digests from the leaf layer up to (not including) the top layer -- the byte layout MerkleTreeProver::prove emits.
+__global__ void gather_queries_kernel(uint32_t* __restrict__ seal, const GatherTree* __restrict__ trees, size_t n_trees,
+                                      const uint32_t* __restrict__ positions, size_t record_words) {
+  size_t q = blockIdx.x, t = blockIdx.y;
+  GatherTree tr = trees[t];
+  uint32_t idx = positions[q] & (tr.rows - 1);
+  uint32_t* o = seal + q * record_words + tr.seal_off;
+  for (uint32_t c = threadIdx.x; c < tr.cols; c += blockDim.x) o[c] = tr.matrix[(size_t)c * tr.rows + idx];
+  o += tr.cols;
+  // path: node indices idx+rows, then halved while >= 2*top_size
+  uint32_t node = idx + tr.rows;
+  uint32_t level = 0;
+  while (node >= 2 * tr.top_size) {
+    if (threadIdx.x < 8) o[level * 8 + threadIdx.x] = tr.nodes[(size_t)(node ^ 1) * 8 + threadIdx.x];
+    node >>= 1;
+    level++;
+  }
+}
+b2z_err launch_gather_queries(b2z_ctx* ctx, uint32_t* seal_dev, const GatherTree* trees_dev, size_t n_trees,
+                              const uint32_t* positions_dev, size_t n_queries, size_t record_words) {
+  gather_queries_kernel<<<dim3((unsigned)n_queries, (unsigned)n_trees), 128, 0, ctx->stream>>>(seal_dev, trees_dev, n_trees, positions_dev,
+                                                                                              record_words);
+  ctx->launches++;
+  B2Z_CUDA(cudaGetLastError());
+  return nullptr;
+}
+
+}  // namespace b2z

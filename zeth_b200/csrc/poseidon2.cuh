@@ -1,0 +1,100 @@
+// Poseidon2 over BabyBear, width 24 (rate 16, output 8): the permutation shared by the device hash kernels
+// (hash_rows / hash_fold) and the host-side Fiat-Shamir transcript.
+//
+// Algorithm = risc0-zkp 3.0.2 core/hash/poseidon2/mod.rs `poseidon2_mix`:
+//   M_E ; 4 x {add rc[24]; x^7; M_E} ; 21 x {add rc to cell 0; x^7 on cell 0; M_I} ; 4 x {add rc; x^7; M_E}
+// with constants from poseidon2_consts.h (generated + KAT-checked by tools/gen_poseidon2_consts.py).
+// The state lives in 24 registers per thread; round constants sit in __constant__ memory in Montgomery form.
+#pragma once
+#include "field.cuh"
+
+namespace b2z {
+
+constexpr int P2_CELLS = 24;
+constexpr int P2_RATE = 16;
+constexpr int P2_OUT = 8;
+constexpr int P2_ROUNDS_HALF_FULL = 4;
+constexpr int P2_ROUNDS_PARTIAL = 21;
+constexpr int P2_NUM_RC = 2 * P2_ROUNDS_HALF_FULL * P2_CELLS + P2_ROUNDS_PARTIAL;  // 213
+
+struct P2Consts {
+  uint32_t rc[P2_NUM_RC];   // Montgomery form
+  uint32_t diag[P2_CELLS];  // Montgomery form
+};
+
+const P2Consts& p2_host_consts();  // transcript.cpp
+
+B2Z_HD uint32_t p2_sbox(uint32_t x) {
+  uint32_t x2 = fp_mul(x, x);
+  uint32_t x3 = fp_mul(x2, x);
+  uint32_t x4 = fp_mul(x2, x2);
+  return fp_mul(x3, x4);
+}
+
+// External linear layer: circ(2*M4, M4, ..., M4) with M4 = [[5,7,1,3],[4,6,1,1],[1,3,5,7],[1,1,4,6]].
+B2Z_HD void p2_m_ext(uint32_t* s) {
+#pragma unroll
+  for (int c = 0; c < P2_CELLS; c += 4) {
+    uint32_t a = s[c], b = s[c + 1], cc = s[c + 2], d = s[c + 3];
+    uint32_t t0 = fp_add(a, b);
+    uint32_t t1 = fp_add(cc, d);
+    uint32_t t2 = fp_add(fp_add(b, b), t1);
+    uint32_t t3 = fp_add(fp_add(d, d), t0);
+    uint32_t t1x2 = fp_add(t1, t1);
+    uint32_t t4 = fp_add(fp_add(t1x2, t1x2), t3);
+    uint32_t t0x2 = fp_add(t0, t0);
+    uint32_t t5 = fp_add(fp_add(t0x2, t0x2), t2);
+    s[c] = fp_add(t3, t5);
+    s[c + 1] = t5;
+    s[c + 2] = fp_add(t2, t4);
+    s[c + 3] = t4;
+  }
+  uint32_t sum0 = 0, sum1 = 0, sum2 = 0, sum3 = 0;
+#pragma unroll
+  for (int c = 0; c < P2_CELLS; c += 4) {
+    sum0 = fp_add(sum0, s[c]);
+    sum1 = fp_add(sum1, s[c + 1]);
+    sum2 = fp_add(sum2, s[c + 2]);
+    sum3 = fp_add(sum3, s[c + 3]);
+  }
+#pragma unroll
+  for (int c = 0; c < P2_CELLS; c += 4) {
+    s[c] = fp_add(s[c], sum0);
+    s[c + 1] = fp_add(s[c + 1], sum1);
+    s[c + 2] = fp_add(s[c + 2], sum2);
+    s[c + 3] = fp_add(s[c + 3], sum3);
+  }
+}
+
+// Internal linear layer: cell_i <- sum(cells) + D_i * cell_i.
+B2Z_HD void p2_m_int(uint32_t* s, const uint32_t* diag) {
+  uint32_t tot = 0;
+#pragma unroll
+  for (int i = 0; i < P2_CELLS; i++) tot = fp_add(tot, s[i]);
+#pragma unroll
+  for (int i = 0; i < P2_CELLS; i++) s[i] = fp_add(tot, fp_mul(diag[i], s[i]));
+}
+
+B2Z_HD void p2_permute(uint32_t* s, const P2Consts& k) {
+  const uint32_t* rc = k.rc;
+  p2_m_ext(s);
+  for (int r = 0; r < P2_ROUNDS_HALF_FULL; r++) {
+#pragma unroll
+    for (int i = 0; i < P2_CELLS; i++) s[i] = p2_sbox(fp_add(s[i], rc[i]));
+    rc += P2_CELLS;
+    p2_m_ext(s);
+  }
+  for (int r = 0; r < P2_ROUNDS_PARTIAL; r++) {
+    s[0] = p2_sbox(fp_add(s[0], rc[0]));
+    rc += 1;
+    p2_m_int(s, k.diag);
+  }
+  for (int r = 0; r < P2_ROUNDS_HALF_FULL; r++) {
+#pragma unroll
+    for (int i = 0; i < P2_CELLS; i++) s[i] = p2_sbox(fp_add(s[i], rc[i]));
+    rc += P2_CELLS;
+    p2_m_ext(s);
+  }
+}
+
+}  // namespace b2z

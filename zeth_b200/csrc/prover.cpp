@@ -1,0 +1,449 @@
+// Segment prover driver: the host-side orchestration of one STARK segment proof on one B200.
+//
+// Call sequence = risc0-circuit-rv32im 4.0.2 SegmentProver::prove over risc0-zkp 3.0.2 prove/{prover,poly_group,
+// merkle,fri,write_iop}.rs: commit code/data groups, draw the accum mix,
+// accumulate, commit accum, eval_check, commit the check group, DEEP evaluations + U coefficients, combos, FRI,
+// 50 queries.  B200-first differences that keep the seal bit-identical:
+//   * the whole pipeline stays on the device; the host only runs the Poseidon2 transcript on 32-byte roots;
+//   * zk_shift is fused into the last iNTT pass; DEEP synthetic division runs on the GPU as a scan;
+//   * all 50 query openings (rows + Merkle paths of every tree) are produced by ONE gather kernel, because the
+//     query positions depend only on the transcript state, not on the opened data.
+#include <cstring>
+
+#include "circuit.h"
+#include "common.h"
+
+namespace b2z {
+
+static const char* PHASE_NAMES[] = {"commit_code", "commit_data", "accumulate", "commit_accum", "eval_check", "commit_check",
+                                    "deep_evaluate", "deep_combos", "fri_commit", "fri_queries", "total"};
+constexpr size_t N_PHASES = sizeof(PHASE_NAMES) / sizeof(PHASE_NAMES[0]);
+const char* phase_name(size_t i) { return i < N_PHASES ? PHASE_NAMES[i] : ""; }
+
+struct PhaseTimer {
+  b2z_ctx* ctx;
+  explicit PhaseTimer(b2z_ctx* c) : ctx(c) {
+    if (ctx->phase_events.size() < N_PHASES) {
+      ctx->phase_events.resize(N_PHASES);
+      for (auto& pr : ctx->phase_events) {
+        cudaEventCreate(&pr.first);
+        cudaEventCreate(&pr.second);
+      }
+    }
+  }
+  void begin(size_t i) { cudaEventRecord(ctx->phase_events[i].first, ctx->stream); }
+  void end(size_t i) { cudaEventRecord(ctx->phase_events[i].second, ctx->stream); }
+  void collect() {
+    ctx->phase_ms.assign(N_PHASES, 0.0);
+    for (size_t i = 0; i < N_PHASES; i++) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, ctx->phase_events[i].first, ctx->phase_events[i].second) == cudaSuccess) ctx->phase_ms[i] = ms;
+    }
+  }
+};
+
+struct DevMem {  // stream-ordered allocations released together
+  b2z_ctx* ctx;
+  std::vector<void*> ptrs;
+  explicit DevMem(b2z_ctx* c) : ctx(c) {}
+  ~DevMem() {
+    for (void* p : ptrs) cudaFreeAsync(p, ctx->stream);
+  }
+  b2z_err alloc(uint32_t** out, size_t words) {
+    void* p = nullptr;
+    B2Z_CUDA(cudaMallocAsync(&p, sizeof(uint32_t) * (words ? words : 1), ctx->stream));
+    ptrs.push_back(p);
+    *out = (uint32_t*)p;
+    return nullptr;
+  }
+  void release(void* p) {
+    for (auto& q : ptrs)
+      if (q == p) {
+        cudaFreeAsync(p, ctx->stream);
+        q = ptrs.back();
+        ptrs.pop_back();
+        return;
+      }
+  }
+};
+
+struct MerkleParams {
+  size_t rows, cols, layers, top_size;
+  MerkleParams(size_t r, size_t c) : rows(r), cols(c) {
+    layers = ilog2(r);
+    size_t top_layer = 0;
+    for (size_t i = 1; i < layers; i++) {
+      if (((size_t)1 << i) > B2Z_QUERIES) break;
+      top_layer = i;
+    }
+    top_size = (size_t)1 << top_layer;
+  }
+  size_t path_words() const { return 8 * (layers - ilog2(top_size)); }
+};
+
+b2z_err merkle_build(b2z_ctx* ctx, uint32_t* nodes, const uint32_t* matrix, size_t rows, size_t cols) {
+  B2Z_TRY(launch_hash_rows(ctx, nodes + 8 * rows, matrix, rows, cols));
+  for (size_t i = ilog2(rows); i-- > 0;) B2Z_TRY(launch_hash_fold(ctx, nodes, (size_t)2 << i, (size_t)1 << i));
+  return nullptr;
+}
+
+struct PolyGroupDev {
+  uint32_t *coeffs = nullptr, *evaluated = nullptr, *nodes = nullptr;
+  size_t count = 0, n = 0;
+};
+
+struct Seal {  // pinned host image of the seal, filled in write order
+  uint32_t* w;
+  size_t pos = 0, cap;
+};
+
+static b2z_err ensure_pinned(b2z_ctx* ctx, size_t words) {
+  if (ctx->pinned_words >= words) return nullptr;
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  ctx->pinned = nullptr;
+  ctx->pinned_words = 0;
+  B2Z_CUDA(cudaMallocHost(&ctx->pinned, sizeof(uint32_t) * words));
+  ctx->pinned_words = words;
+  return nullptr;
+}
+
+// PolyGroup::new + merkle.commit: coeffs (bit-reversed, shifted) -> LDE, natural-order coeffs, Merkle tree, top layer + root
+static b2z_err poly_group_commit(b2z_ctx* ctx, DevMem& mem, PolyGroupDev& pg, uint32_t* coeffs, size_t count, unsigned po2, Seal& seal,
+                                 HostRng& rng) {
+  size_t n = (size_t)1 << po2, domain = 4 * n;
+  pg.coeffs = coeffs;
+  pg.count = count;
+  pg.n = n;
+  B2Z_TRY(mem.alloc(&pg.evaluated, count * domain));
+  B2Z_TRY(launch_evaluate(ctx, pg.evaluated, coeffs, count, po2 + 2, 2));
+  B2Z_TRY(launch_bit_reverse(ctx, coeffs, count, po2));
+  B2Z_TRY(mem.alloc(&pg.nodes, 2 * domain * 8));
+  B2Z_TRY(merkle_build(ctx, pg.nodes, pg.evaluated, domain, count));
+  MerkleParams mp(domain, count);
+  B2Z_REQUIRE(seal.pos + 8 * mp.top_size <= seal.cap, "seal overflow");
+  B2Z_CUDA(cudaMemcpyAsync(seal.w + seal.pos, pg.nodes + 8 * mp.top_size, 32 * mp.top_size, cudaMemcpyDeviceToHost, ctx->stream));
+  uint32_t* root = seal.w + seal.cap;  // scratch after the seal image (ensure_pinned reserves 64 extra words)
+  B2Z_CUDA(cudaMemcpyAsync(root, pg.nodes + 8, 32, cudaMemcpyDeviceToHost, ctx->stream));
+  B2Z_CUDA(cudaStreamSynchronize(ctx->stream));
+  seal.pos += 8 * mp.top_size;
+  rng.mix(root);
+  return nullptr;
+}
+
+// prover.rs make_coeffs + commit_group
+static b2z_err commit_group(b2z_ctx* ctx, DevMem& mem, PolyGroupDev& pg, const uint32_t* witness, size_t count, unsigned po2, Seal& seal,
+                            HostRng& rng) {
+  size_t n = (size_t)1 << po2;
+  uint32_t* coeffs = nullptr;
+  B2Z_TRY(mem.alloc(&coeffs, count * n));
+  B2Z_CUDA(cudaMemcpyAsync(coeffs, witness, 4 * count * n, cudaMemcpyDeviceToDevice, ctx->stream));
+  B2Z_TRY(launch_interpolate(ctx, coeffs, count, po2, /*fuse_zk_shift=*/true));
+  return poly_group_commit(ctx, mem, pg, coeffs, count, po2, seal, rng);
+}
+
+// unique interpolant through (x_i, fx_i) -> monomial coefficients (core/poly.rs poly_interpolate)
+static void poly_interpolate(Fp4* out, const Fp4* x, const Fp4* fx, size_t size) {
+  Fp4 dd[16], basis[17];
+  for (size_t i = 0; i < size; i++) dd[i] = fx[i];
+  for (size_t j = 1; j < size; j++)
+    for (size_t i = size - 1; i >= j; i--) dd[i] = fp4_mul(fp4_sub(dd[i], dd[i - 1]), fp4_inv(fp4_sub(x[i], x[i - j])));
+  for (size_t i = 0; i < size; i++) out[i] = fp4_zero();
+  basis[0] = fp4_one();
+  size_t blen = 1;
+  for (size_t j = 0; j < size; j++) {
+    for (size_t i = 0; i < blen; i++) out[i] = fp4_add(out[i], fp4_mul(dd[j], basis[i]));
+    basis[blen] = fp4_zero();
+    for (size_t i = blen; i > 0; i--) basis[i] = fp4_sub(basis[i - 1], fp4_mul(basis[i], x[j]));
+    basis[0] = fp4_neg(fp4_mul(basis[0], x[j]));
+    blen++;
+  }
+}
+
+static void hash_info(const uint8_t* info, uint32_t* dg) {
+  uint32_t e[16];
+  for (int i = 0; i < 16; i++) e[i] = fp_from_u32(info[i]);
+  host_hash_elem_slice(e, 16, dg);
+}
+
+b2z_err eval_check_launch(b2z_ctx* ctx, const b2z_circuit* c, uint32_t* check, const uint32_t* const groups[3], const uint32_t* globals_dev,
+                          const uint32_t* mix_dev, const Fp4& poly_mix, unsigned po2);
+b2z_err mix_pow_table(b2z_ctx* ctx, uint32_t* tab, const Fp4& start, const Fp4& mix, size_t n);
+
+b2z_err prove_segment_device(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, const uint32_t* code_dev, const uint32_t* data_dev,
+                             const uint32_t* globals_host, const uint32_t* accum_noise_dev, size_t zk_rows, uint32_t* seal_host,
+                             size_t* seal_words_out) {
+  B2Z_REQUIRE(po2 >= 1 && po2 <= 24, "po2 out of range");
+  B2Z_REQUIRE(c->library != nullptr, "circuit kernels not loaded");
+  const size_t n = (size_t)1 << po2, domain = 4 * n;
+  B2Z_REQUIRE(zk_rows < n, "zk_rows must be smaller than the trace");
+  const size_t wa = c->group_size[0], wc = c->group_size[1], wd = c->group_size[2];
+  const size_t gsz = c->globals_size, msz = c->mix_size;
+  const size_t seal_words = circuit_seal_words(c, po2);
+  B2Z_TRY(ensure_pinned(ctx, seal_words + 64 + 4 * (c->n_taps + 64)));
+  Seal seal{ctx->pinned, 0, seal_words};
+  uint32_t* scratch = ctx->pinned + seal_words + 8;  // [root(8)] [eval_u ...]
+  DevMem mem(ctx);
+  PhaseTimer tm(ctx);
+  HostRng rng;
+  uint32_t dg[8];
+  tm.begin(10);
+
+  static const uint8_t PROOF_SYSTEM_INFO[16] = {'R', 'I', 'S', 'C', '0', '_', 'S', 'T', 'A', 'R', 'K', ':', 'v', '1', '_', '_'};
+  hash_info(PROOF_SYSTEM_INFO, dg);
+  rng.mix(dg);
+  hash_info(c->info, dg);
+  rng.mix(dg);
+  // header = globals || po2
+  memcpy(seal.w, globals_host, 4 * gsz);
+  seal.w[gsz] = fp_from_u32(po2);
+  host_hash_elem_slice(seal.w, gsz + 1, dg);
+  rng.mix(dg);
+  seal.pos = gsz + 1;
+  uint32_t* globals_dev = nullptr;
+  B2Z_TRY(mem.alloc(&globals_dev, gsz + 1));
+  B2Z_CUDA(cudaMemcpyAsync(globals_dev, seal.w, 4 * gsz, cudaMemcpyHostToDevice, ctx->stream));
+
+  PolyGroupDev pg[3], check_pg;
+  tm.begin(0);
+  B2Z_TRY(commit_group(ctx, mem, pg[B2Z_GROUP_CODE], code_dev, wc, po2, seal, rng));
+  tm.end(0);
+  tm.begin(1);
+  B2Z_TRY(commit_group(ctx, mem, pg[B2Z_GROUP_DATA], data_dev, wd, po2, seal, rng));
+  tm.end(1);
+
+  std::vector<uint32_t> mix_host(msz + 1);
+  for (size_t i = 0; i < msz; i++) mix_host[i] = rng.random_elem();
+  uint32_t* mix_dev = nullptr;
+  B2Z_TRY(mem.alloc(&mix_dev, msz + 1));
+  B2Z_CUDA(cudaMemcpyAsync(mix_dev, mix_host.data(), 4 * msz, cudaMemcpyHostToDevice, ctx->stream));
+  tm.begin(2);
+  uint32_t* accum = nullptr;
+  B2Z_TRY(mem.alloc(&accum, wa * n));
+  B2Z_TRY(launch_accum(ctx, accum, data_dev, c->accum_col_dev, c->accum_col.size(), mix_dev, accum_noise_dev, po2, zk_rows));
+  tm.end(2);
+  tm.begin(3);
+  {
+    // the accum witness buffer itself becomes the coefficient buffer (no extra copy)
+    B2Z_TRY(launch_interpolate(ctx, accum, wa, po2, true));
+    B2Z_TRY(poly_group_commit(ctx, mem, pg[B2Z_GROUP_ACCUM], accum, wa, po2, seal, rng));
+  }
+  tm.end(3);
+
+  // ---- finalize ----
+  Fp4 poly_mix = rng.random_ext();
+  uint32_t* check = nullptr;
+  B2Z_TRY(mem.alloc(&check, 4 * domain));
+  tm.begin(4);
+  {
+    const uint32_t* groups[3] = {pg[0].evaluated, pg[1].evaluated, pg[2].evaluated};
+    B2Z_TRY(eval_check_launch(ctx, c, check, groups, globals_dev, mix_dev, poly_mix, po2));
+  }
+  tm.end(4);
+  tm.begin(5);
+  B2Z_TRY(launch_interpolate(ctx, check, 4, po2 + 2, false));
+  // bit-reversed 4N coefficients per component = 4 quarters of N: the 16 x N check group, no data movement
+  B2Z_TRY(poly_group_commit(ctx, mem, check_pg, check, B2Z_CHECK_SIZE, po2, seal, rng));
+  tm.end(5);
+
+  tm.begin(6);
+  Fp4 z = rng.random_ext();
+  uint32_t back_one = rou_rev(po2);
+  const size_t n_taps = c->n_taps, n_regs = c->reg_group.size(), n_combos = c->n_combos;
+  const size_t n_evals = n_taps + B2Z_CHECK_SIZE;
+  std::vector<Fp4> all_xs(n_evals);
+  std::vector<uint32_t> which(n_evals);
+  Fp4 z_pow = fp4_pow(z, B2Z_EXT_SIZE);
+  {
+    std::vector<uint32_t> back_pows;
+    for (size_t t = 0; t < n_taps; t++) {
+      uint32_t b = c->tap_back[t];
+      while (back_pows.size() <= b) back_pows.push_back(back_pows.empty() ? MONT_ONE : fp_mul(back_pows.back(), back_one));
+      which[t] = c->tap_offset[t];
+      all_xs[t] = fp4_mul_fp(z, back_pows[b]);
+    }
+    for (size_t i = 0; i < B2Z_CHECK_SIZE; i++) {
+      which[n_taps + i] = (uint32_t)i;
+      all_xs[n_taps + i] = z_pow;
+    }
+  }
+  uint32_t *which_dev = nullptr, *xs_dev = nullptr, *evals_dev = nullptr;
+  B2Z_TRY(mem.alloc(&which_dev, n_evals));
+  B2Z_TRY(mem.alloc(&xs_dev, 4 * n_evals));
+  B2Z_TRY(mem.alloc(&evals_dev, 4 * n_evals));
+  B2Z_CUDA(cudaMemcpyAsync(which_dev, which.data(), 4 * n_evals, cudaMemcpyHostToDevice, ctx->stream));
+  B2Z_CUDA(cudaMemcpyAsync(xs_dev, all_xs.data(), 16 * n_evals, cudaMemcpyHostToDevice, ctx->stream));
+  {
+    size_t pos = 0;
+    for (int g = 0; g < 3; g++) {
+      size_t start = pos;
+      while (pos < n_taps && c->tap_group[pos] == (uint32_t)g) pos++;
+      B2Z_TRY(launch_evaluate_any(ctx, pg[g].coeffs, po2, which_dev + start, xs_dev + 4 * start, pos - start, evals_dev + 4 * start));
+    }
+    B2Z_TRY(launch_evaluate_any(ctx, check_pg.coeffs, po2, which_dev + n_taps, xs_dev + 4 * n_taps, B2Z_CHECK_SIZE, evals_dev + 4 * n_taps));
+  }
+  Fp4* eval_u = reinterpret_cast<Fp4*>(scratch + 8);
+  B2Z_CUDA(cudaMemcpyAsync(eval_u, evals_dev, 16 * n_evals, cudaMemcpyDeviceToHost, ctx->stream));
+  B2Z_CUDA(cudaStreamSynchronize(ctx->stream));
+  B2Z_REQUIRE(seal.pos + 4 * n_evals <= seal.cap, "seal overflow");
+  Fp4* coeff_u = reinterpret_cast<Fp4*>(seal.w + seal.pos);
+  for (size_t r = 0; r < n_regs; r++) {
+    size_t p0 = c->reg_tap_pos[r];
+    B2Z_REQUIRE(c->reg_size[r] <= 16, "register with more than 16 taps");
+    poly_interpolate(coeff_u + p0, all_xs.data() + p0, eval_u + p0, c->reg_size[r]);
+  }
+  for (size_t i = 0; i < B2Z_CHECK_SIZE; i++) coeff_u[n_taps + i] = eval_u[n_taps + i];
+  seal.pos += 4 * n_evals;
+  host_hash_elem_slice(reinterpret_cast<uint32_t*>(coeff_u), 4 * n_evals, dg);
+  rng.mix(dg);
+  tm.end(6);
+
+  tm.begin(7);
+  Fp4 mixv = rng.random_ext();
+  uint32_t* combos = nullptr;
+  B2Z_TRY(mem.alloc(&combos, 4 * n * (n_combos + 1)));
+  B2Z_CUDA(cudaMemsetAsync(combos, 0, 16 * n * (n_combos + 1), ctx->stream));
+  {
+    // combo id of every column, device-resident
+    std::vector<uint32_t> ids(n_regs + B2Z_CHECK_SIZE);
+    for (size_t r = 0; r < n_regs; r++) ids[r] = c->reg_combo[r];
+    for (size_t i = 0; i < B2Z_CHECK_SIZE; i++) ids[n_regs + i] = (uint32_t)n_combos;
+    uint32_t* ids_dev = nullptr;
+    B2Z_TRY(mem.alloc(&ids_dev, ids.size()));
+    B2Z_CUDA(cudaMemcpyAsync(ids_dev, ids.data(), 4 * ids.size(), cudaMemcpyHostToDevice, ctx->stream));
+    Fp4 cur_mix = fp4_one();
+    size_t r = 0;
+    for (int g = 0; g < 3; g++) {
+      size_t gs = c->group_size[g];
+      B2Z_TRY(launch_mix_poly_coeffs(ctx, combos, cur_mix, mixv, pg[g].coeffs, ids_dev + r, gs, n));
+      cur_mix = fp4_mul(cur_mix, fp4_pow(mixv, gs));
+      r += gs;
+    }
+    B2Z_TRY(launch_mix_poly_coeffs(ctx, combos, cur_mix, mixv, check_pg.coeffs, ids_dev + n_regs, B2Z_CHECK_SIZE, n));
+  }
+  {
+    // U polynomials per combo (same sums the verifier forms as combo_u), subtracted from the low coefficients
+    std::vector<Fp4> combo_u(c->tot_combo_backs + 1, fp4_zero());
+    Fp4 cur = fp4_one();
+    size_t cur_pos = 0;
+    for (size_t r = 0; r < n_regs; r++) {
+      for (size_t i = 0; i < c->reg_size[r]; i++) {
+        Fp4& dst = combo_u[c->combo_begin[c->reg_combo[r]] + i];
+        dst = fp4_add(dst, fp4_mul(cur, coeff_u[cur_pos + i]));
+      }
+      cur = fp4_mul(cur, mixv);
+      cur_pos += c->reg_size[r];
+    }
+    for (size_t i = 0; i < B2Z_CHECK_SIZE; i++) {
+      combo_u[c->tot_combo_backs] = fp4_add(combo_u[c->tot_combo_backs], fp4_mul(cur, coeff_u[cur_pos]));
+      cur_pos++;
+      cur = fp4_mul(cur, mixv);
+    }
+    uint32_t *cu_dev = nullptr, *rem_dev = nullptr;
+    B2Z_TRY(mem.alloc(&cu_dev, 4 * combo_u.size()));
+    B2Z_TRY(mem.alloc(&rem_dev, 4 * (c->tot_combo_backs + 2)));
+    B2Z_CUDA(cudaMemcpyAsync(cu_dev, combo_u.data(), 16 * combo_u.size(), cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<uint32_t> back_pows;
+    size_t nrem = 0;
+    for (size_t k = 0; k < n_combos; k++) {
+      size_t b0 = c->combo_begin[k], b1 = c->combo_begin[k + 1];
+      B2Z_TRY(launch_sub_lowcoeffs(ctx, combos + 4 * k * n, cu_dev + 4 * b0, b1 - b0));
+      for (size_t j = b0; j < b1; j++) {
+        uint32_t b = c->combo_backs[j];
+        while (back_pows.size() <= b) back_pows.push_back(back_pows.empty() ? MONT_ONE : fp_mul(back_pows.back(), back_one));
+        B2Z_TRY(launch_poly_divide(ctx, combos + 4 * k * n, n, fp4_mul_fp(z, back_pows[b]), rem_dev + 4 * nrem++));
+      }
+    }
+    B2Z_TRY(launch_sub_lowcoeffs(ctx, combos + 4 * n_combos * n, cu_dev + 4 * c->tot_combo_backs, 1));
+    B2Z_TRY(launch_poly_divide(ctx, combos + 4 * n_combos * n, n, z_pow, rem_dev + 4 * nrem++));
+  }
+  uint32_t* final_coeffs = nullptr;
+  B2Z_TRY(mem.alloc(&final_coeffs, 4 * n));
+  B2Z_TRY(launch_sum_extelem(ctx, final_coeffs, combos, n, n_combos + 1));
+  B2Z_TRY(launch_bit_reverse(ctx, final_coeffs, 4, po2));
+  tm.end(7);
+
+  // ---- FRI (prove/fri.rs) ----
+  tm.begin(8);
+  struct Round {
+    uint32_t *evaluated, *nodes;
+    size_t domain;
+  };
+  std::vector<Round> rounds;
+  uint32_t* coeffs = final_coeffs;
+  size_t size = n;
+  while (size > B2Z_FRI_MIN_DEGREE) {
+    Round r;
+    r.domain = size * B2Z_INV_RATE;
+    B2Z_TRY(mem.alloc(&r.evaluated, 4 * r.domain));
+    B2Z_TRY(launch_evaluate(ctx, r.evaluated, coeffs, 4, ilog2(r.domain), 2));
+    size_t rows = r.domain / B2Z_FRI_FOLD;
+    B2Z_TRY(mem.alloc(&r.nodes, 2 * rows * 8));
+    B2Z_TRY(merkle_build(ctx, r.nodes, r.evaluated, rows, B2Z_FRI_FOLD * 4));
+    MerkleParams mp(rows, 64);
+    B2Z_REQUIRE(seal.pos + 8 * mp.top_size <= seal.cap, "seal overflow");
+    B2Z_CUDA(cudaMemcpyAsync(seal.w + seal.pos, r.nodes + 8 * mp.top_size, 32 * mp.top_size, cudaMemcpyDeviceToHost, ctx->stream));
+    B2Z_CUDA(cudaMemcpyAsync(scratch, r.nodes + 8, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    B2Z_CUDA(cudaStreamSynchronize(ctx->stream));
+    seal.pos += 8 * mp.top_size;
+    rng.mix(scratch);
+    Fp4 fold_mix = rng.random_ext();
+    uint32_t* out = nullptr;
+    B2Z_TRY(mem.alloc(&out, 4 * size / B2Z_FRI_FOLD));
+    B2Z_TRY(launch_fri_fold(ctx, out, coeffs, fold_mix, size / B2Z_FRI_FOLD));
+    coeffs = out;
+    size /= B2Z_FRI_FOLD;
+    rounds.push_back(r);
+  }
+  {
+    uint32_t* fin = nullptr;
+    B2Z_TRY(mem.alloc(&fin, 4 * size));
+    B2Z_CUDA(cudaMemcpyAsync(fin, coeffs, 16 * size, cudaMemcpyDeviceToDevice, ctx->stream));
+    B2Z_TRY(launch_bit_reverse(ctx, fin, 4, ilog2(size)));
+    B2Z_REQUIRE(seal.pos + 4 * size <= seal.cap, "seal overflow");
+    B2Z_CUDA(cudaMemcpyAsync(seal.w + seal.pos, fin, 16 * size, cudaMemcpyDeviceToHost, ctx->stream));
+    B2Z_CUDA(cudaStreamSynchronize(ctx->stream));
+    host_hash_elem_slice(seal.w + seal.pos, 4 * size, dg);
+    seal.pos += 4 * size;
+    rng.mix(dg);
+  }
+  tm.end(8);
+
+  // ---- queries: positions from the transcript, one gather kernel for every tree ----
+  tm.begin(9);
+  {
+    std::vector<uint32_t> positions(B2Z_QUERIES);
+    for (auto& p : positions) p = rng.random_bits(ilog2(domain));
+    std::vector<GatherTree> trees;
+    size_t off = 0;
+    auto add_tree = [&](const uint32_t* matrix, const uint32_t* nodes, size_t rows, size_t cols) {
+      MerkleParams mp(rows, cols);
+      GatherTree t{matrix, nodes, (uint32_t)rows, (uint32_t)cols, (uint32_t)mp.top_size, (uint32_t)off, 0};
+      trees.push_back(t);
+      off += cols + mp.path_words();
+    };
+    for (int g = 0; g < 3; g++) add_tree(pg[g].evaluated, pg[g].nodes, domain, pg[g].count);
+    add_tree(check_pg.evaluated, check_pg.nodes, domain, B2Z_CHECK_SIZE);
+    for (auto& r : rounds) add_tree(r.evaluated, r.nodes, r.domain / B2Z_FRI_FOLD, 64);
+    size_t record_words = off;
+    B2Z_REQUIRE(seal.pos + B2Z_QUERIES * record_words == seal.cap, "seal length mismatch");
+    uint32_t *pos_dev = nullptr, *q_dev = nullptr;
+    GatherTree* trees_dev = nullptr;
+    B2Z_TRY(mem.alloc(&pos_dev, B2Z_QUERIES));
+    B2Z_TRY(mem.alloc(&q_dev, B2Z_QUERIES * record_words));
+    B2Z_TRY(mem.alloc(reinterpret_cast<uint32_t**>(&trees_dev), (sizeof(GatherTree) * trees.size() + 3) / 4));
+    B2Z_CUDA(cudaMemcpyAsync(pos_dev, positions.data(), 4 * B2Z_QUERIES, cudaMemcpyHostToDevice, ctx->stream));
+    B2Z_CUDA(cudaMemcpyAsync(trees_dev, trees.data(), sizeof(GatherTree) * trees.size(), cudaMemcpyHostToDevice, ctx->stream));
+    B2Z_TRY(launch_gather_queries(ctx, q_dev, trees_dev, trees.size(), pos_dev, B2Z_QUERIES, record_words));
+    B2Z_CUDA(cudaMemcpyAsync(seal.w + seal.pos, q_dev, 4 * B2Z_QUERIES * record_words, cudaMemcpyDeviceToHost, ctx->stream));
+    seal.pos += B2Z_QUERIES * record_words;
+  }
+  tm.end(9);
+  tm.end(10);
+  B2Z_CUDA(cudaStreamSynchronize(ctx->stream));
+  tm.collect();
+  memcpy(seal_host, seal.w, 4 * seal_words);
+  if (seal_words_out) *seal_words_out = seal_words;
+  return nullptr;
+}
+
+}  // namespace b2z

@@ -1,0 +1,81 @@
+// Host side of the Fiat-Shamir transcript: Poseidon2 sponge, hash_pair and Poseidon2Rng on the CPU.
+//
+// The transcript of one seal needs a few hundred permutations (latency, not throughput), so it runs on the host
+// between kernel phases exactly where upstream runs it (risc0-zkp 3.0.2 prove/write_iop.rs,
+// core/hash/poseidon2/{mod,rng}.rs; SURVEY.md A.4, scope row a17).  It shares the permutation source with the
+// device kernels (poseidon2.cuh) -- this file is product code and does not use anything under oracle/.
+#include <cstring>
+
+#include "common.h"
+#include "poseidon2.cuh"
+#include "poseidon2_consts.h"
+
+namespace b2z {
+
+const P2Consts& p2_host_consts() {
+  static P2Consts k = [] {
+    P2Consts c;
+    for (int i = 0; i < P2_NUM_RC; i++) c.rc[i] = fp_from_u32(P2_ROUND_CONSTANTS[i]);
+    for (int i = 0; i < P2_CELLS; i++) c.diag[i] = fp_from_u32(P2_M_INT_DIAG[i]);
+    return c;
+  }();
+  return k;
+}
+
+void host_poseidon2_mix(uint32_t* s) { p2_permute(s, p2_host_consts()); }
+
+void host_hash_elem_slice(const uint32_t* in, size_t n, uint32_t* digest) {
+  uint32_t st[P2_CELLS] = {};
+  size_t unmixed = 0;
+  for (size_t i = 0; i < n; i++) {
+    st[unmixed++] = in[i];
+    if (unmixed == P2_RATE) {
+      host_poseidon2_mix(st);
+      unmixed = 0;
+    }
+  }
+  if (unmixed != 0 || n == 0) {
+    for (size_t i = unmixed; i < P2_RATE; i++) st[i] = 0;
+    host_poseidon2_mix(st);
+  }
+  memcpy(digest, st, 32);
+}
+
+void host_hash_pair(const uint32_t* a, const uint32_t* b, uint32_t* digest) {
+  uint32_t st[P2_CELLS] = {};
+  memcpy(st, a, 32);
+  memcpy(st + 8, b, 32);
+  host_poseidon2_mix(st);
+  memcpy(digest, st, 32);
+}
+
+void HostRng::mix(const uint32_t* digest) {
+  if (pool_used != 0) {
+    host_poseidon2_mix(cells);
+    pool_used = 0;
+  }
+  for (int i = 0; i < 8; i++) cells[i] = fp_add(cells[i], digest[i]);
+  host_poseidon2_mix(cells);
+}
+uint32_t HostRng::random_elem() {
+  if (pool_used == P2_RATE) {
+    host_poseidon2_mix(cells);
+    pool_used = 0;
+  }
+  return cells[pool_used++];
+}
+Fp4 HostRng::random_ext() {
+  Fp4 r;
+  for (int i = 0; i < 4; i++) r.e[i] = random_elem();
+  return r;
+}
+uint32_t HostRng::random_bits(unsigned bits) {
+  uint32_t val = fp_to_u32(random_elem());
+  for (int i = 0; i < 3; i++) {
+    uint32_t nv = fp_to_u32(random_elem());
+    if (val == 0) val = nv;
+  }
+  return (uint32_t)((((uint64_t)1) << bits) - 1) & val;
+}
+
+}  // namespace b2z
