@@ -1,0 +1,57 @@
+"""N > 1 host logic on CPU: world_size-2 gloo run of the segment-table broadcast, the round-robin partition and the
+seal gather.  The seals here come from the oracle (no GPU in this test)."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from zeth_b200 import shard
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_segments, seal_words, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dev = torch.device("cpu")
+    table = np.array([[i, 1000 + i, 10] for i in range(n_segments)], dtype=np.int64) if rank == 0 else None
+    table = shard.broadcast_segment_table(table, dev)
+    mine = shard.partition(n_segments, world, rank)
+    local = {i: (np.arange(seal_words, dtype=np.uint32) * np.uint32(table[i][1])) for i in mine}
+    seals = shard.gather_seals(local, n_segments, seal_words, dev)
+    if rank == 0:
+        ok = all(np.array_equal(seals[i], np.arange(seal_words, dtype=np.uint32) * np.uint32(1000 + i)) for i in range(n_segments))
+        q.put((ok, [int(t[1]) for t in table]))
+    dist.destroy_process_group()
+
+
+def test_partition_covers_every_segment_once():
+    for world in (1, 2, 4, 8):
+        for n in (1, 7, 500):
+            parts = [shard.partition(n, world, r) for r in range(world)]
+            assert sorted(sum(parts, [])) == list(range(n))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def test_broadcast_and_gather_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 5, 64, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    ok, seeds = q.get(timeout=5)
+    assert ok and seeds == [1000, 1001, 1002, 1003, 1004]
