@@ -14,6 +14,7 @@ b2z_err eval_check_launch(b2z_ctx* ctx, const b2z_circuit* c, uint32_t* check, c
 b2z_err witgen_launch(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, uint32_t* code, uint32_t* data, uint32_t* globals_dev,
                       uint32_t* accum_noise_dev, uint64_t seed, size_t zk_rows);
 const char* phase_name(size_t i);
+void ntt_release_tables(b2z_ctx* ctx);
 }  // namespace b2z
 using namespace b2z;
 
@@ -50,6 +51,7 @@ b2z_err b2z_destroy(b2z_ctx* ctx) {
   if (!ctx) return nullptr;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  ntt_release_tables(ctx);
   for (int i = 0; i <= MAX_PO2; i++) {
     if (ctx->tw_fwd[i]) cudaFree(ctx->tw_fwd[i]);
     if (ctx->tw_rev[i]) cudaFree(ctx->tw_rev[i]);

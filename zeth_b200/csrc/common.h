@@ -67,6 +67,8 @@ b2z_err launch_hash_fold(b2z_ctx* ctx, uint32_t* nodes, size_t in_size, size_t o
 b2z_err launch_fri_fold(b2z_ctx* ctx, uint32_t* out, const uint32_t* in, const Fp4& mix, size_t out_count);
 b2z_err launch_evaluate_any(b2z_ctx* ctx, const uint32_t* coeffs, unsigned po2, const uint32_t* which, const uint32_t* xs,
                             size_t eval_count, uint32_t* out);
+b2z_err launch_evaluate_any_host(b2z_ctx* ctx, const uint32_t* coeffs, unsigned po2, const uint32_t* which_host, const Fp4* xs_host,
+                                 size_t eval_count, uint32_t* out);
 b2z_err launch_mix_poly_coeffs(b2z_ctx* ctx, uint32_t* out, const Fp4& mix_start, const Fp4& mix, const uint32_t* in,
                                const uint32_t* combos_dev, size_t input_size, size_t count);
 b2z_err launch_add_elem(b2z_ctx* ctx, uint32_t* out, const uint32_t* a, const uint32_t* b, size_t n);

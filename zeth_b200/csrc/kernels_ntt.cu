@@ -1,193 +1,423 @@
-// BabyBear NTT kernels: batch_interpolate_ntt (DIF, natural -> bit-reversed, optional fused zk_shift),
-// batch_expand_into_evaluate_ntt / batch_evaluate_ntt (DIT, bit-reversed -> natural), bit_reverse, zk_shift.
+// BabyBear NTT kernels: batch_interpolate_ntt (natural -> bit-reversed, 1/n, optional fused zk_shift),
+// batch_expand_into_evaluate_ntt / batch_evaluate_ntt (bit-reversed -> natural), bit_reverse, zk_shift.
 //
-// Semantics follow risc0-zkp 3.0.2 core/ntt.rs + hal/cpu.rs (scope rows a5-a8).  Data layout is
-// column-major [count][n].  A transform of 2^logn points runs as at most two passes over HBM: each CTA stages a
-// tile of 2^T elements in shared memory and performs up to T butterfly layers on it.  The tile of the "far"
-// pass is [2^B strided rows] x [2^LB contiguous elements] so that every global access is a >= 64-byte run.
+// Semantics follow risc0-zkp 3.0.2 core/ntt.rs + hal/cpu.rs (scope rows a5-a8); layout is column-major
+// [count][n].  The implementation is NOT upstream's layer-by-layer recursion.  A 2^L-point transform is factored
+// (Cooley-Tukey, L = R1 + R2 + ...) into passes of R <= 8 bits; pass k works on the bits above the previous passes and
+// is preceded by one element-wise "twist" multiplication w^(rev(i_hi) * k_lo) (table lookup, coalesced), after which
+// every 2^R-point sub-transform uses the SAME twiddles.  That makes all twiddles warp-uniform:
+//   * a CTA stages a tile of [2^R points] x [32 lanes] in shared memory; lane = one independent sub-transform
+//     (32 adjacent low-index positions for strided passes, 32 consecutive contiguous rows for the first pass, with a
+//     padded pitch so that every shared-memory access of a warp is conflict-free);
+//   * each thread runs radix-16 butterflies on 16 registers with the sixteenth roots of unity as constant-bank
+//     operands; one uniform twist between the two radix-16 groups of a pass;
+//   * the expand step (out[i] = in[i >> 2]) is folded into the first pass's loads, 1/n and the zk_shift factor
+//     3^rev(j) into the last inverse pass's stores.
+// Columns are processed in chunks sized to stay inside the 126 MB L2, so that the passes after the first one read and
+// write L2-resident lines and HBM sees close to the compulsory traffic (1 read of the input, 1 write of the output).
+#include <map>
+#include <tuple>
+
 #include "common.h"
 
 namespace b2z {
 
-__global__ void build_twiddles_kernel(uint32_t* tw, uint32_t w, size_t half) {
-  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i < half) tw[i] = fp_pow(w, i);
-}
+// sixteenth roots of unity (Montgomery form): c_w16[j] = w16^j, c_w16i[j] = w16^-j, j < 8
+__constant__ uint32_t c_w16[8];
+__constant__ uint32_t c_w16i[8];
+static bool g_w16_uploaded[16] = {};
+
 __global__ void build_pow3rev_kernel(uint32_t* tab, unsigned bits) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i < ((size_t)1 << bits)) tab[i] = fp_pow(MONT_THREE, bit_rev((uint32_t)i, bits));
 }
+// twist table for a pass boundary: T[i] = w^(rev_b(i >> a) * (i & (2^a - 1))), w = primitive 2^(a+b)-th root (or inverse)
+__global__ void build_twist_kernel(uint32_t* tab, uint32_t w, unsigned a, unsigned b) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= ((size_t)1 << (a + b))) return;
+  uint64_t e = (uint64_t)bit_rev((uint32_t)(i >> a), b) * (uint64_t)(i & (((size_t)1 << a) - 1));
+  tab[i] = fp_pow(w, e);
+}
 
-b2z_err ensure_tables(b2z_ctx* ctx, unsigned po2, bool fwd, bool rev, bool pow3) {
-  B2Z_REQUIRE(po2 <= MAX_PO2, "transform size exceeds 2^26");
-  size_t n = (size_t)1 << po2, half = n / 2;
-  if (fwd && !ctx->tw_fwd[po2]) {
-    B2Z_CUDA(cudaMalloc(&ctx->tw_fwd[po2], sizeof(uint32_t) * (half ? half : 1)));
-    if (half) build_twiddles_kernel<<<(unsigned)((half + 255) / 256), 256, 0, ctx->stream>>>(ctx->tw_fwd[po2], rou_fwd(po2), half);
+struct TwistKey {
+  unsigned a, b;
+  bool inv;
+  bool operator<(const TwistKey& o) const { return std::tie(a, b, inv) < std::tie(o.a, o.b, o.inv); }
+};
+struct NttTables {
+  std::map<TwistKey, uint32_t*> twist;
+};
+static std::map<b2z_ctx*, NttTables> g_tables;  // one context per thread (see b2z.h); guarded by that contract
+
+static b2z_err get_twist(b2z_ctx* ctx, unsigned a, unsigned b, bool inv, const uint32_t** out) {
+  NttTables& t = g_tables[ctx];
+  TwistKey k{a, b, inv};
+  auto it = t.twist.find(k);
+  if (it == t.twist.end()) {
+    uint32_t* p = nullptr;
+    size_t n = (size_t)1 << (a + b);
+    B2Z_CUDA(cudaMalloc(&p, 4 * n));
+    uint32_t w = inv ? rou_rev(a + b) : rou_fwd(a + b);
+    build_twist_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(p, w, a, b);
     ctx->launches++;
+    B2Z_CUDA(cudaGetLastError());
+    it = t.twist.emplace(k, p).first;
   }
-  if (rev && !ctx->tw_rev[po2]) {
-    B2Z_CUDA(cudaMalloc(&ctx->tw_rev[po2], sizeof(uint32_t) * (half ? half : 1)));
-    if (half) build_twiddles_kernel<<<(unsigned)((half + 255) / 256), 256, 0, ctx->stream>>>(ctx->tw_rev[po2], rou_rev(po2), half);
-    ctx->launches++;
+  *out = it->second;
+  return nullptr;
+}
+void ntt_release_tables(b2z_ctx* ctx) {
+  auto it = g_tables.find(ctx);
+  if (it == g_tables.end()) return;
+  for (auto& kv : it->second.twist) cudaFree(kv.second);
+  g_tables.erase(it);
+}
+
+b2z_err ensure_tables(b2z_ctx* ctx, unsigned po2, bool, bool, bool pow3) {
+  B2Z_REQUIRE(po2 <= MAX_PO2, "transform size exceeds 2^26");
+  if (ctx->device < 16 && !g_w16_uploaded[ctx->device]) {
+    uint32_t w[8], wi[8], g = rou_fwd(4), gi = rou_rev(4);
+    w[0] = wi[0] = MONT_ONE;
+    for (int j = 1; j < 8; j++) {
+      w[j] = fp_mul(w[j - 1], g);
+      wi[j] = fp_mul(wi[j - 1], gi);
+    }
+    B2Z_CUDA(cudaMemcpyToSymbol(c_w16, w, sizeof w));
+    B2Z_CUDA(cudaMemcpyToSymbol(c_w16i, wi, sizeof wi));
+    g_w16_uploaded[ctx->device] = true;
   }
   if (pow3 && !ctx->pow3rev[po2]) {
+    size_t n = (size_t)1 << po2;
     B2Z_CUDA(cudaMalloc(&ctx->pow3rev[po2], sizeof(uint32_t) * n));
     build_pow3rev_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->pow3rev[po2], po2);
     ctx->launches++;
+    B2Z_CUDA(cudaGetLastError());
   }
-  B2Z_CUDA(cudaGetLastError());
   return nullptr;
 }
 
-// One pass over butterfly layers (s_lo + t) for t in [t_begin, B] of a 2^logn-point transform, every column.
-//   tile element (mid, lo): global index = hi << (s_lo + B) | mid << s_lo | (lo_blk << LB | lo)
-//   INVERSE = false: decimation in time   a' = a + w b, b' = a - w b, layers ascending
-//   INVERSE = true : decimation in frequency a' = a + b, b' = (a - b) w, layers descending
-// `ebits` > 0 (forward first pass only): the tile is loaded from `in` at index (gidx >> ebits) -- the expand step.
-template <bool INVERSE>
-__global__ void ntt_pass_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ in, const uint32_t* __restrict__ tw,
-                                const uint32_t* __restrict__ scale_tab, uint32_t scale, unsigned logn, unsigned s_lo, unsigned B,
-                                unsigned LB, unsigned t_begin, unsigned ebits, int apply_scale) {
-  extern __shared__ uint32_t sm[];
-  const unsigned tile_log = B + LB;
-  const unsigned tile = 1u << tile_log;
-  const size_t n = (size_t)1 << logn;
-  const unsigned lo_blocks_log = s_lo - LB;
-  const size_t tile_id = blockIdx.x;
-  const size_t hi = tile_id >> lo_blocks_log;
-  const unsigned lo_blk = (unsigned)(tile_id & ((1u << lo_blocks_log) - 1));
-  const size_t col = blockIdx.y;
-  const size_t base = (hi << (s_lo + B)) | ((size_t)lo_blk << LB);
-  const unsigned lo_mask = (1u << LB) - 1;
-  uint32_t* colp = out + col * n;
+// ---- register-level radix-2^Q butterflies with constant sixteenth-root twiddles ----
+// forward: decimation in time, layers FIRST..Q (in place; positions hold the bit-reversed-order input)
+template <int Q, int FIRST>
+__device__ __forceinline__ void dit_base(uint32_t* v) {
+#pragma unroll
+  for (int s = FIRST; s <= Q; s++) {
+    const int half = 1 << (s - 1);
+#pragma unroll
+    for (int blk = 0; blk < (1 << Q); blk += 2 * half) {
+#pragma unroll
+      for (int j = 0; j < half; j++) {
+        uint32_t a = v[blk + j];
+        uint32_t b = v[blk + j + half];
+        if (j != 0) b = fp_mul(b, c_w16[j << (4 - s)]);
+        v[blk + j] = fp_add(a, b);
+        v[blk + j + half] = fp_sub(a, b);
+      }
+    }
+  }
+}
+// inverse: decimation in frequency, layers Q..1, inverse twiddles (natural in -> bit-reversed out)
+template <int Q>
+__device__ __forceinline__ void dif_base(uint32_t* v) {
+#pragma unroll
+  for (int s = Q; s >= 1; s--) {
+    const int half = 1 << (s - 1);
+#pragma unroll
+    for (int blk = 0; blk < (1 << Q); blk += 2 * half) {
+#pragma unroll
+      for (int j = 0; j < half; j++) {
+        uint32_t a = v[blk + j];
+        uint32_t b = v[blk + j + half];
+        v[blk + j] = fp_add(a, b);
+        uint32_t d = fp_sub(a, b);
+        v[blk + j + half] = j != 0 ? fp_mul(d, c_w16i[j << (4 - s)]) : d;
+      }
+    }
+  }
+}
 
-  for (unsigned e = threadIdx.x; e < tile; e += blockDim.x) {
-    size_t g = base + ((size_t)(e >> LB) << s_lo) + (e & lo_mask);
-    sm[e] = ebits ? in[col * (n >> ebits) + (g >> ebits)] : in[col * n + g];
+// One radix group over bits [g_lo, g_lo + Q) of the R-bit point index, for all lanes of the tile.
+//   smem address of (point p, lane l) = p * pitch_p + l * pitch_l
+//   pre/post twist (intra-pass, warp-uniform): multiply point p by twist[p] after (forward) / before (inverse) the group
+template <int Q, bool INV, int FIRST>
+__device__ __forceinline__ void radix_group(uint32_t* sm, unsigned R, unsigned g_lo, unsigned pitch_p, unsigned pitch_l,
+                                            const uint32_t* __restrict__ twist, unsigned lane, unsigned warp, unsigned nwarps) {
+  const unsigned sets = 1u << (R - Q);
+  for (unsigned set = warp; set < sets; set += nwarps) {
+    // set index -> the point bits outside [g_lo, g_lo+Q)
+    unsigned low = set & ((1u << g_lo) - 1), high = set >> g_lo;
+    unsigned p0 = (high << (g_lo + Q)) | low;
+    uint32_t v[1 << Q];
+#pragma unroll
+    for (int j = 0; j < (1 << Q); j++) {
+      unsigned p = p0 | ((unsigned)j << g_lo);
+      uint32_t x = sm[p * pitch_p + lane * pitch_l];
+      if (INV && twist) x = fp_mul(x, __ldg(twist + p));
+      v[j] = x;
+    }
+    if (INV) dif_base<Q>(v);
+    else dit_base<Q, FIRST>(v);
+#pragma unroll
+    for (int j = 0; j < (1 << Q); j++) {
+      unsigned p = p0 | ((unsigned)j << g_lo);
+      uint32_t x = v[j];
+      if (!INV && twist) x = fp_mul(x, __ldg(twist + p));
+      sm[p * pitch_p + lane * pitch_l] = x;
+    }
+  }
+}
+
+template <bool INV, int FIRST>
+__device__ __forceinline__ void radix_dispatch(unsigned Q, uint32_t* sm, unsigned R, unsigned g_lo, unsigned pitch_p, unsigned pitch_l,
+                                               const uint32_t* twist, unsigned lane, unsigned warp, unsigned nwarps) {
+  switch (Q) {
+    case 4: radix_group<4, INV, FIRST>(sm, R, g_lo, pitch_p, pitch_l, twist, lane, warp, nwarps); break;
+    case 3: radix_group<3, INV, FIRST>(sm, R, g_lo, pitch_p, pitch_l, twist, lane, warp, nwarps); break;
+    case 2: radix_group<2, INV, FIRST>(sm, R, g_lo, pitch_p, pitch_l, twist, lane, warp, nwarps); break;
+    case 1: radix_group<1, INV, FIRST>(sm, R, g_lo, pitch_p, pitch_l, twist, lane, warp, nwarps); break;
+    default: break;
+  }
+}
+
+struct PassArgs {
+  uint32_t* out;
+  const uint32_t* in;
+  const uint32_t* pass_twist;   // inter-pass twist table of 2^(s_lo + R) entries (nullptr for the first pass)
+  const uint32_t* group_twist;  // intra-pass twist table of 2^R entries (nullptr when the pass has one group)
+  const uint32_t* scale_tab;    // optional per-position factor on the final inverse store (zk_shift), period 2^logn
+  uint32_t scale;               // final inverse scale (1/n), applied when apply_scale
+  unsigned logn;                // per-column transform size
+  unsigned s_lo, R, q1;         // bits below this pass, bits of this pass, size of the first radix group
+  unsigned ebits;               // expand bits folded into the first forward pass's loads
+  int apply_scale;
+  size_t total;                 // total elements of the launch (columns * n)
+};
+
+// rows mode (s_lo == 0): tile = 32 consecutive rows of 2^R contiguous points, lane = row, pitch (2^R + 1)
+// strided mode          : tile = 2^R points at stride 2^s_lo x 32 adjacent positions, lane = position, pitch_p = 32
+template <bool INV, int FIRST>
+__global__ void __launch_bounds__(256) ntt_pass_kernel(PassArgs a) {
+  extern __shared__ uint32_t sm[];
+  const unsigned R = a.R, npts = 1u << R;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const bool rows_mode = (a.s_lo == 0);
+  const unsigned pitch_p = rows_mode ? 1u : 32u;
+  const unsigned pitch_l = rows_mode ? (npts + 1) : 1u;
+  const size_t tile_elems = (size_t)npts * 32;
+  size_t base;       // global index of (point 0, lane 0)
+  if (rows_mode) {
+    base = (size_t)blockIdx.x * tile_elems;
+  } else {
+    // tiles enumerate (hi, lo_blk): hi over total / 2^(s_lo+R), lo_blk over 2^s_lo / 32
+    const unsigned lo_blocks_log = a.s_lo - 5;
+    size_t hi = (size_t)blockIdx.x >> lo_blocks_log;
+    size_t lo_blk = (size_t)blockIdx.x & (((size_t)1 << lo_blocks_log) - 1);
+    base = (hi << (a.s_lo + R)) | (lo_blk << 5);
+  }
+  const size_t twist_mask = ((size_t)1 << (a.s_lo + R)) - 1;
+
+  // ---- load (forward: inter-pass twist applied here) ----
+  if (rows_mode) {
+    for (unsigned e = threadIdx.x; e < tile_elems; e += blockDim.x) {
+      size_t g = base + e;
+      uint32_t x = 0;
+      if (g < a.total) x = a.ebits ? __ldg(a.in + (g >> a.ebits)) : a.in[g];
+      sm[(e >> R) * pitch_l + (e & (npts - 1))] = x;
+    }
+  } else {
+    for (unsigned e = threadIdx.x; e < tile_elems; e += blockDim.x) {
+      unsigned p = e >> 5, l = e & 31;
+      size_t g = base + ((size_t)p << a.s_lo) + l;
+      uint32_t x = a.in[g];
+      if (!INV && a.pass_twist) x = fp_mul(x, __ldg(a.pass_twist + (g & twist_mask)));
+      sm[p * 32 + l] = x;
+    }
   }
   __syncthreads();
 
-  const unsigned pairs = tile >> 1;
-  if (!INVERSE) {
-    for (unsigned t = t_begin; t <= B; t++) {
-      const unsigned half = 1u << (t - 1);
-      const unsigned s = s_lo + t;
-      for (unsigned p = threadIdx.x; p < pairs; p += blockDim.x) {
-        unsigned lo = p & lo_mask, pm = p >> LB;
-        unsigned jm = pm & (half - 1);
-        unsigned m0 = ((pm >> (t - 1)) << t) | jm;
-        unsigned i0 = (m0 << LB) | lo, i1 = i0 + (half << LB);
-        size_t j = ((size_t)jm << s_lo) | ((size_t)lo_blk << LB) | lo;
-        uint32_t w = tw[j << (logn - s)];
-        uint32_t a = sm[i0], b = fp_mul(sm[i1], w);
-        sm[i0] = fp_add(a, b);
-        sm[i1] = fp_sub(a, b);
-      }
+  // ---- compute: at most two radix groups (R <= 8) ----
+  const unsigned q1 = a.q1, q2 = R - q1;
+  if (!INV) {
+    radix_dispatch<false, FIRST>(q1, sm, R, 0, pitch_p, pitch_l, q2 ? a.group_twist : nullptr, lane, warp, nwarps);
+    if (q2) {
       __syncthreads();
+      radix_dispatch<false, 1>(q2, sm, R, q1, pitch_p, pitch_l, nullptr, lane, warp, nwarps);
     }
   } else {
-    for (unsigned t = B; t >= t_begin; t--) {
-      const unsigned half = 1u << (t - 1);
-      const unsigned s = s_lo + t;
-      for (unsigned p = threadIdx.x; p < pairs; p += blockDim.x) {
-        unsigned lo = p & lo_mask, pm = p >> LB;
-        unsigned jm = pm & (half - 1);
-        unsigned m0 = ((pm >> (t - 1)) << t) | jm;
-        unsigned i0 = (m0 << LB) | lo, i1 = i0 + (half << LB);
-        size_t j = ((size_t)jm << s_lo) | ((size_t)lo_blk << LB) | lo;
-        uint32_t w = tw[j << (logn - s)];
-        uint32_t a = sm[i0], b = sm[i1];
-        sm[i0] = fp_add(a, b);
-        sm[i1] = fp_mul(fp_sub(a, b), w);
-      }
+    if (q2) {
+      radix_dispatch<true, 1>(q2, sm, R, q1, pitch_p, pitch_l, nullptr, lane, warp, nwarps);
       __syncthreads();
     }
+    radix_dispatch<true, 1>(q1, sm, R, 0, pitch_p, pitch_l, q2 ? a.group_twist : nullptr, lane, warp, nwarps);
   }
+  __syncthreads();
 
-  for (unsigned e = threadIdx.x; e < tile; e += blockDim.x) {
-    size_t g = base + ((size_t)(e >> LB) << s_lo) + (e & lo_mask);
-    uint32_t v = sm[e];
-    if (apply_scale) {
-      v = fp_mul(v, scale);
-      if (scale_tab) v = fp_mul(v, scale_tab[g]);
+  // ---- store (inverse: inter-pass twist / final scale applied here) ----
+  if (rows_mode) {
+    for (unsigned e = threadIdx.x; e < tile_elems; e += blockDim.x) {
+      size_t g = base + e;
+      if (g >= a.total) continue;
+      uint32_t x = sm[(e >> R) * pitch_l + (e & (npts - 1))];
+      if (a.apply_scale) {
+        x = fp_mul(x, a.scale);
+        if (a.scale_tab) x = fp_mul(x, __ldg(a.scale_tab + (g & (((size_t)1 << a.logn) - 1))));
+      }
+      a.out[g] = x;
     }
-    colp[g] = v;
+  } else {
+    for (unsigned e = threadIdx.x; e < tile_elems; e += blockDim.x) {
+      unsigned p = e >> 5, l = e & 31;
+      size_t g = base + ((size_t)p << a.s_lo) + l;
+      uint32_t x = sm[p * 32 + l];
+      if (INV && a.pass_twist) x = fp_mul(x, __ldg(a.pass_twist + (g & twist_mask)));
+      a.out[g] = x;
+    }
   }
 }
 
-struct NttPlan {
-  unsigned T;  // log2 tile elements of the contiguous pass
-  unsigned B2; // layers handled by the strided pass (0 = single pass)
-  unsigned LB; // log2 contiguous run of the strided pass
-  unsigned threads;
-};
-static NttPlan make_plan(unsigned logn) {
-  NttPlan p;
-  if (logn <= 13) {
-    p.T = logn;
-    p.B2 = 0;
-    p.LB = 0;
-  } else {
-    unsigned need = (logn + 4 + 1) / 2;
-    p.T = need < 13 ? 13 : need;
-    if (p.T > 15) p.T = 15;
-    p.B2 = logn - p.T;
-    p.LB = p.T - p.B2;
+// split logn into passes of <= 8 bits, first pass largest; every later pass needs s_lo >= 5 (32 adjacent lanes)
+static void plan_passes(unsigned logn, unsigned* R, unsigned* np) {
+  unsigned n = (logn + 7) / 8;
+  if (n == 0) n = 1;
+  if (n == 1) {
+    R[0] = logn;
+    *np = 1;
+    return;
   }
-  p.threads = p.T <= 13 ? 256 : (p.T == 14 ? 512 : 1024);
-  return p;
+  unsigned base = logn / n, rem = logn % n;
+  for (unsigned i = 0; i < n; i++) R[i] = base + (i < rem ? 1 : 0);
+  if (R[0] < 5) {  // logn = 9: 5 + 4
+    unsigned need = 5 - R[0];
+    R[0] += need;
+    R[n - 1] -= need;
+  }
+  *np = n;
 }
 
-template <bool INV>
-static b2z_err launch_pass(b2z_ctx* ctx, uint32_t* out, const uint32_t* in, const uint32_t* tw, const uint32_t* scale_tab,
-                           uint32_t scale, unsigned logn, unsigned s_lo, unsigned B, unsigned LB, unsigned t_begin, unsigned ebits,
-                           int apply_scale, size_t count, unsigned threads) {
-  size_t tiles = ((size_t)1 << logn) >> (B + LB);
-  size_t smem = sizeof(uint32_t) << (B + LB);
-  static bool attr_set[2] = {false, false};
-  if (smem > 48 * 1024 && !attr_set[INV]) {
-    B2Z_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set[INV] = true;
-  }
-  // gridDim.y is limited to 65535 columns; the prover never exceeds a few thousand
-  B2Z_REQUIRE(count <= 65535, "too many columns for one NTT launch");
-  dim3 grid((unsigned)tiles, (unsigned)count);
-  unsigned tile = 1u << (B + LB);
-  unsigned th = threads;
-  while (th > 32 && th > tile / 2) th >>= 1;
-  ntt_pass_kernel<INV><<<grid, th, smem, ctx->stream>>>(out, in, tw, scale_tab, scale, logn, s_lo, B, LB, t_begin, ebits, apply_scale);
+static size_t chunk_columns(size_t count, unsigned logn) {
+  // keep one chunk's working set (in place: 4 B * cols * n) around 40 MB so the later passes hit in the 126 MB L2
+  size_t bytes_per_col = (size_t)4 << logn;
+  size_t c = (40u << 20) / bytes_per_col;
+  if (c < 1) c = 1;
+  return c < count ? c : count;
+}
+
+template <bool INV, int FIRST>
+static b2z_err launch_one(b2z_ctx* ctx, const PassArgs& a) {
+  const unsigned npts = 1u << a.R;
+  size_t smem = a.s_lo == 0 ? sizeof(uint32_t) * 32 * (npts + 1) : sizeof(uint32_t) * 32 * npts;
+  size_t tile_elems = (size_t)npts * 32;
+  size_t tiles = (a.total + tile_elems - 1) / tile_elems;
+  if (a.s_lo != 0) B2Z_REQUIRE(a.total % tile_elems == 0, "strided NTT pass needs whole tiles");
+  unsigned threads = 256;
+  ntt_pass_kernel<INV, FIRST><<<(unsigned)tiles, threads, smem, ctx->stream>>>(a);
   ctx->launches++;
   B2Z_CUDA(cudaGetLastError());
   return nullptr;
 }
 
-b2z_err launch_interpolate(b2z_ctx* ctx, uint32_t* io, size_t count, unsigned po2, bool fuse_zk_shift) {
-  if (count == 0) return nullptr;
-  B2Z_TRY(ensure_tables(ctx, po2, false, true, fuse_zk_shift));
-  uint32_t norm = fp_inv(fp_from_u32((uint32_t)((uint64_t)1 << po2) % P));
-  const uint32_t* tab = fuse_zk_shift ? ctx->pow3rev[po2] : nullptr;
-  if (po2 == 0) return nullptr;
-  NttPlan p = make_plan(po2);
-  if (p.B2) B2Z_TRY(launch_pass<true>(ctx, io, io, ctx->tw_rev[po2], nullptr, 0, po2, p.T, p.B2, p.LB, 1, 0, 0, count, p.threads));
-  B2Z_TRY(launch_pass<true>(ctx, io, io, ctx->tw_rev[po2], tab, norm, po2, 0, p.T, 0, 1, 0, 1, count, p.threads));
-  return nullptr;
-}
-
+// forward transform of `count` columns: out (2^logn per column) from in (2^(logn - ebits) per column when expanding)
 b2z_err launch_evaluate(b2z_ctx* ctx, uint32_t* out, const uint32_t* in, size_t count, unsigned out_po2, unsigned expand_bits) {
   if (count == 0) return nullptr;
-  B2Z_TRY(ensure_tables(ctx, out_po2, true, false, false));
-  NttPlan p = make_plan(out_po2);
-  B2Z_REQUIRE(expand_bits <= p.T, "expand_bits larger than the first tile");
+  B2Z_TRY(ensure_tables(ctx, out_po2, false, false, false));
+  const unsigned logn = out_po2;
   bool expanding = (in != out);
-  // contiguous pass: layers expand_bits+1 .. T, loading through the expand map when `in` is the short array
-  B2Z_TRY(launch_pass<false>(ctx, out, in, ctx->tw_fwd[out_po2], nullptr, 0, out_po2, 0, p.T, 0, expand_bits + 1,
-                             expanding ? expand_bits : 0, 0, count, p.threads));
-  if (p.B2) B2Z_TRY(launch_pass<false>(ctx, out, out, ctx->tw_fwd[out_po2], nullptr, 0, out_po2, p.T, p.B2, p.LB, 1, 0, 0, count, p.threads));
+  if (logn == 0) {
+    if (expanding) B2Z_CUDA(cudaMemcpyAsync(out, in, 4 * count, cudaMemcpyDeviceToDevice, ctx->stream));
+    return nullptr;
+  }
+  unsigned R[8], np = 0;
+  plan_passes(logn, R, &np);
+  B2Z_REQUIRE(expand_bits <= (R[0] < 4 ? R[0] : 4), "expand_bits larger than the first radix group");
+  const uint32_t* pass_tw[8] = {};
+  const uint32_t* grp_tw[8] = {};
+  unsigned s_lo = 0;
+  for (unsigned k = 0; k < np; k++) {
+    unsigned q1 = R[k] < 4 ? R[k] : 4;
+    if (k > 0) B2Z_TRY(get_twist(ctx, s_lo, R[k], false, &pass_tw[k]));
+    if (R[k] > q1) B2Z_TRY(get_twist(ctx, q1, R[k] - q1, false, &grp_tw[k]));
+    s_lo += R[k];
+  }
+  const size_t n = (size_t)1 << logn;
+  const size_t cc = chunk_columns(count, logn);
+  for (size_t c0 = 0; c0 < count; c0 += cc) {
+    size_t cols = (count - c0 < cc) ? count - c0 : cc;
+    s_lo = 0;
+    for (unsigned k = 0; k < np; k++) {
+      PassArgs a{};
+      a.out = out + c0 * n;
+      a.in = (k == 0 && expanding) ? in + c0 * (n >> expand_bits) : out + c0 * n;
+      a.pass_twist = pass_tw[k];
+      a.group_twist = grp_tw[k];
+      a.scale_tab = nullptr;
+      a.scale = 0;
+      a.logn = logn;
+      a.s_lo = s_lo;
+      a.R = R[k];
+      a.q1 = R[k] < 4 ? R[k] : 4;
+      a.ebits = (k == 0 && expanding) ? expand_bits : 0;
+      a.apply_scale = 0;
+      a.total = cols * n;
+      unsigned first = (k == 0) ? expand_bits + 1 : 1;  // skipped layers are valid for in-place evaluate_ntt(expand_bits) too
+      switch (first) {
+        case 1: B2Z_TRY((launch_one<false, 1>(ctx, a))); break;
+        case 2: B2Z_TRY((launch_one<false, 2>(ctx, a))); break;
+        case 3: B2Z_TRY((launch_one<false, 3>(ctx, a))); break;
+        case 4: B2Z_TRY((launch_one<false, 4>(ctx, a))); break;
+        default: B2Z_TRY((launch_one<false, 5>(ctx, a))); break;
+      }
+      s_lo += R[k];
+    }
+  }
   return nullptr;
 }
 
-__global__ void bit_reverse_kernel(uint32_t* io, unsigned bits, size_t total) {
+b2z_err launch_interpolate(b2z_ctx* ctx, uint32_t* io, size_t count, unsigned po2, bool fuse_zk_shift) {
+  if (count == 0) return nullptr;
+  B2Z_TRY(ensure_tables(ctx, po2, false, false, fuse_zk_shift));
+  const unsigned logn = po2;
+  if (logn == 0) return nullptr;
+  uint32_t norm = fp_inv(fp_from_u32((uint32_t)(((uint64_t)1 << po2) % P)));
+  unsigned R[8], np = 0;
+  plan_passes(logn, R, &np);
+  const uint32_t* pass_tw[8] = {};
+  const uint32_t* grp_tw[8] = {};
+  unsigned s_los[8];
+  unsigned s_lo = 0;
+  for (unsigned k = 0; k < np; k++) {
+    unsigned q1 = R[k] < 4 ? R[k] : 4;
+    s_los[k] = s_lo;
+    if (k > 0) B2Z_TRY(get_twist(ctx, s_lo, R[k], true, &pass_tw[k]));
+    if (R[k] > q1) B2Z_TRY(get_twist(ctx, q1, R[k] - q1, true, &grp_tw[k]));
+    s_lo += R[k];
+  }
+  const size_t n = (size_t)1 << logn;
+  const size_t cc = chunk_columns(count, logn);
+  for (size_t c0 = 0; c0 < count; c0 += cc) {
+    size_t cols = (count - c0 < cc) ? count - c0 : cc;
+    for (unsigned kk = np; kk-- > 0;) {
+      PassArgs a{};
+      a.out = io + c0 * n;
+      a.in = io + c0 * n;
+      a.pass_twist = pass_tw[kk];
+      a.group_twist = grp_tw[kk];
+      a.scale_tab = (kk == 0 && fuse_zk_shift) ? ctx->pow3rev[po2] : nullptr;
+      a.scale = norm;
+      a.logn = logn;
+      a.s_lo = s_los[kk];
+      a.R = R[kk];
+      a.q1 = R[kk] < 4 ? R[kk] : 4;
+      a.ebits = 0;
+      a.apply_scale = (kk == 0);
+      a.total = cols * n;
+      B2Z_TRY((launch_one<true, 1>(ctx, a)));
+    }
+  }
+  return nullptr;
+}
+
+// ---- bit reversal and stand-alone zk_shift ----
+__global__ void bit_reverse_small_kernel(uint32_t* io, unsigned bits, size_t total) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= total) return;
   size_t col = i >> bits;
@@ -200,10 +430,39 @@ __global__ void bit_reverse_kernel(uint32_t* io, unsigned bits, size_t total) {
     p[r] = a;
   }
 }
+// bits >= 10: index = (hi:5)(mid)(lo:5).  The 32x32 tile {hi, lo} of a given mid maps onto the tile of rev(mid) with
+// (hi', lo') = (rev lo, rev hi): a CTA swaps the two tiles through shared memory with coalesced 128-byte rows.
+__global__ void __launch_bounds__(256) bit_reverse_tile_kernel(uint32_t* io, unsigned bits) {
+  __shared__ uint32_t sa[32][33], sb[32][33];
+  const unsigned mbits = bits - 10;
+  const uint32_t mid = blockIdx.x, rmid = bit_rev(mid, mbits);
+  if (mid > rmid) return;
+  uint32_t* p = io + ((size_t)blockIdx.y << bits);
+  const unsigned c = threadIdx.x & 31, r0 = threadIdx.x >> 5;
+  for (unsigned r = r0; r < 32; r += 8) {
+    sa[r][c] = p[((size_t)r << (bits - 5)) | ((size_t)mid << 5) | c];
+    if (mid != rmid) sb[r][c] = p[((size_t)r << (bits - 5)) | ((size_t)rmid << 5) | c];
+  }
+  __syncthreads();
+  const unsigned rc = bit_rev(c, 5);
+  for (unsigned r = r0; r < 32; r += 8) {
+    const unsigned rr = bit_rev(r, 5);
+    if (mid != rmid) {
+      p[((size_t)r << (bits - 5)) | ((size_t)rmid << 5) | c] = sa[rc][rr];
+      p[((size_t)r << (bits - 5)) | ((size_t)mid << 5) | c] = sb[rc][rr];
+    } else {
+      p[((size_t)r << (bits - 5)) | ((size_t)mid << 5) | c] = sa[rc][rr];
+    }
+  }
+}
 b2z_err launch_bit_reverse(b2z_ctx* ctx, uint32_t* io, size_t count, unsigned po2) {
   size_t total = count << po2;
   if (!total || po2 == 0) return nullptr;
-  bit_reverse_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(io, po2, total);
+  if (po2 < 10 || count > 65535) {
+    bit_reverse_small_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(io, po2, total);
+  } else {
+    bit_reverse_tile_kernel<<<dim3(1u << (po2 - 10), (unsigned)count), 256, 0, ctx->stream>>>(io, po2);
+  }
   ctx->launches++;
   B2Z_CUDA(cudaGetLastError());
   return nullptr;

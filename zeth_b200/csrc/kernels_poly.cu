@@ -34,67 +34,152 @@ b2z_err launch_fri_fold(b2z_ctx* ctx, uint32_t* out, const uint32_t* in, const F
 }
 
 // ---------------- batch_evaluate_any ----------------
-// out[i] = sum_j coeffs[which[i]][j] * xs[i]^j.  Grid (chunks, evals): thread t of a chunk owns coefficients
-// j = chunk_base + t + k*T (coalesced), runs Horner in x^T, then scales by x^(chunk_base + t); block tree-reduces;
-// partial sums are combined with one atomic-free second kernel.
+// out[i] = sum_j coeffs[which[i]][j] * xs[i]^j (natural-order coefficients).
+// Evaluations that share the same point x (all taps with the same `back`) share one table of powers x^j (ext, built
+// once per distinct x, L2 resident); each evaluation is then a base-field x ext dot product: one coalesced read of the
+// column, 4 modular multiplies per coefficient.  A block handles EA_GROUP evaluations of the same x over one chunk of
+// coefficients so that every loaded power is reused EA_GROUP times from registers.
 constexpr unsigned EA_THREADS = 256;
-constexpr unsigned EA_PER_THREAD = 16;
-__global__ void __launch_bounds__(EA_THREADS) evaluate_any_kernel(const uint32_t* __restrict__ coeffs, unsigned po2,
-                                                                  const uint32_t* __restrict__ which, const uint32_t* __restrict__ xs,
-                                                                  uint32_t* __restrict__ partial, unsigned chunks) {
-  __shared__ Fp4 red[EA_THREADS];
-  const size_t n = (size_t)1 << po2;
-  const unsigned ev = blockIdx.y, chunk = blockIdx.x, t = threadIdx.x;
-  const uint32_t* p = coeffs + (size_t)which[ev] * n;
-  Fp4 x = fp4_make(xs[4 * ev], xs[4 * ev + 1], xs[4 * ev + 2], xs[4 * ev + 3]);
-  const size_t chunk_elems = (size_t)EA_THREADS * EA_PER_THREAD;
-  const size_t base = chunk * chunk_elems;
-  Fp4 xT = fp4_pow(x, EA_THREADS);
-  Fp4 acc = fp4_zero();
-#pragma unroll
-  for (int k = EA_PER_THREAD - 1; k >= 0; k--) {
-    size_t j = base + t + (size_t)k * EA_THREADS;
-    uint32_t c = j < n ? __ldg(p + j) : 0u;
-    acc = fp4_add_fp(fp4_mul(acc, xT), c);
+constexpr unsigned EA_PER_THREAD = 8;
+constexpr unsigned EA_GROUP = 8;
+constexpr unsigned EA_POW_RUN = 64;
+__global__ void ea_powers_kernel(uint32_t* __restrict__ pw, Fp4 x, size_t n) {
+  size_t b = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) * EA_POW_RUN;
+  if (b >= n) return;
+  Fp4 cur = fp4_pow(x, b);
+  for (size_t j = b; j < b + EA_POW_RUN && j < n; j++) {
+    *reinterpret_cast<uint4*>(pw + 4 * j) = make_uint4(cur.e[0], cur.e[1], cur.e[2], cur.e[3]);
+    cur = fp4_mul(cur, x);
   }
-  acc = fp4_mul(acc, fp4_pow(x, base + t));
-  red[t] = acc;
-  __syncthreads();
-  for (unsigned s = EA_THREADS / 2; s > 0; s >>= 1) {
-    if (t < s) red[t] = fp4_add(red[t], red[t + s]);
+}
+// group g: evaluations evs[g*EA_GROUP .. +EA_GROUP) (column ids in cols[], -1 padded), all at the point of table pw_of[g]
+__global__ void __launch_bounds__(EA_THREADS) ea_dot_kernel(const uint32_t* __restrict__ coeffs, size_t n,
+                                                            const int* __restrict__ cols, const uint32_t* const* __restrict__ pw_of,
+                                                            uint32_t* __restrict__ partial, unsigned chunks) {
+  __shared__ Fp4 red[EA_THREADS];
+  const unsigned g = blockIdx.y, chunk = blockIdx.x, t = threadIdx.x;
+  const uint32_t* pw = pw_of[g];
+  int col[EA_GROUP];
+#pragma unroll
+  for (unsigned e = 0; e < EA_GROUP; e++) col[e] = cols[g * EA_GROUP + e];
+  Fp4 acc[EA_GROUP];
+#pragma unroll
+  for (unsigned e = 0; e < EA_GROUP; e++) acc[e] = fp4_zero();
+  const size_t base = (size_t)chunk * EA_THREADS * EA_PER_THREAD;
+#pragma unroll 2
+  for (unsigned k = 0; k < EA_PER_THREAD; k++) {
+    size_t j = base + t + (size_t)k * EA_THREADS;
+    if (j >= n) break;
+    uint4 pv = *reinterpret_cast<const uint4*>(pw + 4 * j);
+#pragma unroll
+    for (unsigned e = 0; e < EA_GROUP; e++) {
+      if (col[e] < 0) continue;
+      uint32_t c = __ldg(coeffs + (size_t)col[e] * n + j);
+      acc[e].e[0] = fp_add(acc[e].e[0], fp_mul(pv.x, c));
+      acc[e].e[1] = fp_add(acc[e].e[1], fp_mul(pv.y, c));
+      acc[e].e[2] = fp_add(acc[e].e[2], fp_mul(pv.z, c));
+      acc[e].e[3] = fp_add(acc[e].e[3], fp_mul(pv.w, c));
+    }
+  }
+  for (unsigned e = 0; e < EA_GROUP; e++) {
+    red[t] = acc[e];
+    __syncthreads();
+    for (unsigned s = EA_THREADS / 2; s > 0; s >>= 1) {
+      if (t < s) red[t] = fp4_add(red[t], red[t + s]);
+      __syncthreads();
+    }
+    if (t == 0) {
+      uint32_t* o = partial + 4 * (((size_t)g * EA_GROUP + e) * chunks + chunk);
+      o[0] = red[0].e[0]; o[1] = red[0].e[1]; o[2] = red[0].e[2]; o[3] = red[0].e[3];
+    }
     __syncthreads();
   }
-  if (t == 0) {
-    uint32_t* o = partial + 4 * ((size_t)ev * chunks + chunk);
-    o[0] = red[0].e[0]; o[1] = red[0].e[1]; o[2] = red[0].e[2]; o[3] = red[0].e[3];
-  }
 }
-__global__ void evaluate_any_reduce_kernel(const uint32_t* __restrict__ partial, uint32_t* __restrict__ out, unsigned chunks,
-                                           size_t evals) {
-  size_t ev = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (ev >= evals) return;
+// out[dst[s]] = sum over chunks of partial[s]
+__global__ void ea_reduce_kernel(const uint32_t* __restrict__ partial, const int* __restrict__ dst, uint32_t* __restrict__ out,
+                                 unsigned chunks, size_t slots) {
+  size_t s = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (s >= slots || dst[s] < 0) return;
   Fp4 tot = fp4_zero();
   for (unsigned c = 0; c < chunks; c++) {
-    const uint32_t* q = partial + 4 * (ev * chunks + c);
+    const uint32_t* q = partial + 4 * (s * chunks + c);
     tot = fp4_add(tot, fp4_make(q[0], q[1], q[2], q[3]));
   }
-  out[4 * ev] = tot.e[0]; out[4 * ev + 1] = tot.e[1]; out[4 * ev + 2] = tot.e[2]; out[4 * ev + 3] = tot.e[3];
+  uint32_t* o = out + 4 * (size_t)dst[s];
+  o[0] = tot.e[0]; o[1] = tot.e[1]; o[2] = tot.e[2]; o[3] = tot.e[3];
 }
+b2z_err launch_evaluate_any_host(b2z_ctx* ctx, const uint32_t* coeffs, unsigned po2, const uint32_t* which_host, const Fp4* xs_host,
+                                 size_t eval_count, uint32_t* out) {
+  if (!eval_count) return nullptr;
+  const size_t n = (size_t)1 << po2;
+  // distinct points
+  std::vector<Fp4> pts;
+  std::vector<std::vector<size_t>> members;
+  for (size_t i = 0; i < eval_count; i++) {
+    size_t k = 0;
+    for (; k < pts.size(); k++)
+      if (fp4_eq(pts[k], xs_host[i])) break;
+    if (k == pts.size()) {
+      pts.push_back(xs_host[i]);
+      members.emplace_back();
+    }
+    members[k].push_back(i);
+  }
+  // groups of EA_GROUP evaluations sharing a point
+  std::vector<int> cols, dst;
+  std::vector<size_t> group_pt;
+  for (size_t k = 0; k < pts.size(); k++)
+    for (size_t m = 0; m < members[k].size(); m += EA_GROUP) {
+      group_pt.push_back(k);
+      for (unsigned e = 0; e < EA_GROUP; e++) {
+        bool ok = m + e < members[k].size();
+        cols.push_back(ok ? (int)which_host[members[k][m + e]] : -1);
+        dst.push_back(ok ? (int)members[k][m + e] : -1);
+      }
+    }
+  const size_t groups = group_pt.size(), slots = groups * EA_GROUP;
+  const size_t chunk_elems = (size_t)EA_THREADS * EA_PER_THREAD;
+  const unsigned chunks = (unsigned)((n + chunk_elems - 1) / chunk_elems);
+  B2Z_REQUIRE(groups <= 65535, "too many evaluation groups for one launch");
+  uint32_t *pw = nullptr, *partial = nullptr;
+  int *cols_dev = nullptr, *dst_dev = nullptr;
+  const uint32_t** pw_of_dev = nullptr;
+  B2Z_CUDA(cudaMallocAsync(&pw, 16 * n * pts.size(), ctx->stream));
+  B2Z_CUDA(cudaMallocAsync(&partial, 16 * slots * chunks, ctx->stream));
+  B2Z_CUDA(cudaMallocAsync(&cols_dev, 4 * slots, ctx->stream));
+  B2Z_CUDA(cudaMallocAsync(&dst_dev, 4 * slots, ctx->stream));
+  B2Z_CUDA(cudaMallocAsync(&pw_of_dev, 8 * groups, ctx->stream));
+  std::vector<const uint32_t*> pw_of(groups);
+  for (size_t g = 0; g < groups; g++) pw_of[g] = pw + 4 * n * group_pt[g];
+  B2Z_CUDA(cudaMemcpyAsync(cols_dev, cols.data(), 4 * slots, cudaMemcpyHostToDevice, ctx->stream));
+  B2Z_CUDA(cudaMemcpyAsync(dst_dev, dst.data(), 4 * slots, cudaMemcpyHostToDevice, ctx->stream));
+  B2Z_CUDA(cudaMemcpyAsync(pw_of_dev, pw_of.data(), 8 * groups, cudaMemcpyHostToDevice, ctx->stream));
+  size_t pthreads = (n + EA_POW_RUN - 1) / EA_POW_RUN;
+  for (size_t k = 0; k < pts.size(); k++) {
+    ea_powers_kernel<<<(unsigned)((pthreads + 127) / 128), 128, 0, ctx->stream>>>(pw + 4 * n * k, pts[k], n);
+    ctx->launches++;
+  }
+  ea_dot_kernel<<<dim3(chunks, (unsigned)groups), EA_THREADS, 0, ctx->stream>>>(coeffs, n, cols_dev, pw_of_dev, partial, chunks);
+  ea_reduce_kernel<<<(unsigned)((slots + 127) / 128), 128, 0, ctx->stream>>>(partial, dst_dev, out, chunks, slots);
+  ctx->launches += 2;
+  B2Z_CUDA(cudaGetLastError());
+  B2Z_CUDA(cudaFreeAsync(pw, ctx->stream));
+  B2Z_CUDA(cudaFreeAsync(partial, ctx->stream));
+  B2Z_CUDA(cudaFreeAsync(cols_dev, ctx->stream));
+  B2Z_CUDA(cudaFreeAsync(dst_dev, ctx->stream));
+  B2Z_CUDA(cudaFreeAsync(pw_of_dev, ctx->stream));
+  return nullptr;
+}
+// device-array form of the C ABI: fetch the (small) which / xs arrays and use the grouped implementation
 b2z_err launch_evaluate_any(b2z_ctx* ctx, const uint32_t* coeffs, unsigned po2, const uint32_t* which, const uint32_t* xs,
                             size_t eval_count, uint32_t* out) {
   if (!eval_count) return nullptr;
-  size_t n = (size_t)1 << po2;
-  size_t chunk_elems = (size_t)EA_THREADS * EA_PER_THREAD;
-  unsigned chunks = (unsigned)((n + chunk_elems - 1) / chunk_elems);
-  B2Z_REQUIRE(eval_count <= 65535, "too many evaluation points for one launch");
-  uint32_t* partial = nullptr;
-  B2Z_CUDA(cudaMallocAsync(&partial, sizeof(uint32_t) * 4 * eval_count * chunks, ctx->stream));
-  evaluate_any_kernel<<<dim3(chunks, (unsigned)eval_count), EA_THREADS, 0, ctx->stream>>>(coeffs, po2, which, xs, partial, chunks);
-  evaluate_any_reduce_kernel<<<(unsigned)((eval_count + 127) / 128), 128, 0, ctx->stream>>>(partial, out, chunks, eval_count);
-  ctx->launches += 2;
-  B2Z_CUDA(cudaGetLastError());
-  B2Z_CUDA(cudaFreeAsync(partial, ctx->stream));
-  return nullptr;
+  std::vector<uint32_t> w(eval_count);
+  std::vector<Fp4> x(eval_count);
+  B2Z_CUDA(cudaMemcpyAsync(w.data(), which, 4 * eval_count, cudaMemcpyDeviceToHost, ctx->stream));
+  B2Z_CUDA(cudaMemcpyAsync(x.data(), xs, 16 * eval_count, cudaMemcpyDeviceToHost, ctx->stream));
+  B2Z_CUDA(cudaStreamSynchronize(ctx->stream));
+  return launch_evaluate_any_host(ctx, coeffs, po2, w.data(), x.data(), eval_count, out);
 }
 
 // ---------------- mix_poly_coeffs ----------------

@@ -266,20 +266,17 @@ b2z_err prove_segment_device(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, c
       all_xs[n_taps + i] = z_pow;
     }
   }
-  uint32_t *which_dev = nullptr, *xs_dev = nullptr, *evals_dev = nullptr;
-  B2Z_TRY(mem.alloc(&which_dev, n_evals));
-  B2Z_TRY(mem.alloc(&xs_dev, 4 * n_evals));
+  uint32_t* evals_dev = nullptr;
   B2Z_TRY(mem.alloc(&evals_dev, 4 * n_evals));
-  B2Z_CUDA(cudaMemcpyAsync(which_dev, which.data(), 4 * n_evals, cudaMemcpyHostToDevice, ctx->stream));
-  B2Z_CUDA(cudaMemcpyAsync(xs_dev, all_xs.data(), 16 * n_evals, cudaMemcpyHostToDevice, ctx->stream));
   {
     size_t pos = 0;
     for (int g = 0; g < 3; g++) {
       size_t start = pos;
       while (pos < n_taps && c->tap_group[pos] == (uint32_t)g) pos++;
-      B2Z_TRY(launch_evaluate_any(ctx, pg[g].coeffs, po2, which_dev + start, xs_dev + 4 * start, pos - start, evals_dev + 4 * start));
+      B2Z_TRY(launch_evaluate_any_host(ctx, pg[g].coeffs, po2, which.data() + start, all_xs.data() + start, pos - start, evals_dev + 4 * start));
     }
-    B2Z_TRY(launch_evaluate_any(ctx, check_pg.coeffs, po2, which_dev + n_taps, xs_dev + 4 * n_taps, B2Z_CHECK_SIZE, evals_dev + 4 * n_taps));
+    B2Z_TRY(launch_evaluate_any_host(ctx, check_pg.coeffs, po2, which.data() + n_taps, all_xs.data() + n_taps, B2Z_CHECK_SIZE,
+                                     evals_dev + 4 * n_taps));
   }
   Fp4* eval_u = reinterpret_cast<Fp4*>(scratch + 8);
   B2Z_CUDA(cudaMemcpyAsync(eval_u, evals_dev, 16 * n_evals, cudaMemcpyDeviceToHost, ctx->stream));
