@@ -210,57 +210,70 @@ __device__ __forceinline__ E emul(E x, E y) {
   r.d = fadd(fadd(fmul(x.a, y.d), fmul(x.b, y.c)), fadd(fmul(x.c, y.b), fmul(x.d, y.a)));
   return r;
 }
-__device__ __forceinline__ E eld(const u32* p) { uint4 v = *reinterpret_cast<const uint4*>(p); return emake(v.x, v.y, v.z, v.w); }
+// loads are volatile asm so that the compiler keeps each tap load next to its use instead of hoisting hundreds of
+// loads to the top of the straight-line program (which costs 255 registers and spills)
+__device__ __forceinline__ u32 ldv(const u32* p) { u32 v; asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+// column load: base pointer of the column (kernel-parameter table, uniform) + 32-bit byte offset of the row
+__device__ __forceinline__ u32 ldc(const u32* col, u32 off) {
+  u32 v;
+  asm volatile("{ .reg .u64 a; cvt.u64.u32 a, %2; add.u64 a, a, %1; ld.global.nc.u32 %0, [a]; }" : "=r"(v) : "l"(col), "r"(off));
+  return v;
+}
+__device__ __forceinline__ E eld(const u32* p) {
+  E r; asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.a), "=r"(r.b), "=r"(r.c), "=r"(r.d) : "l"(p)); return r;
+}
 )CUDA";
 
-static void emit_fp_steps(std::ostringstream& o, const std::vector<b2z_circuit::Step>& steps, const b2z_circuit* c, bool trace_domain,
-                          std::vector<uint8_t>* is_ext_out) {
-  // emits the fp-valued steps; returns per-var ext flags
+// Straight-line emission.  Leaf steps (Const, ConstExt, Get, GetGlobal) are never materialised as variables: they are
+// re-emitted as expressions at every use, so a tap value lives only for the instruction that consumes it.  Interior
+// steps (Add/Sub/Mul) become one `const` variable each, in program order.
+struct Emitter {
+  const b2z_circuit* c;
+  bool trace_domain;  // witgen: taps address the trace (stride 1) instead of the 4x LDE (stride 4)
+  std::vector<std::string> expr;
   std::vector<uint8_t> is_ext;
-  size_t nf = 0;
-  auto nm = [&](size_t v) { return std::string(is_ext[v] ? "e" : "f") + std::to_string(v); };
-  for (const auto& s : steps) {
+  unsigned max_back = 0;
+  std::string operand(size_t v) const { return expr[v]; }
+  void step(std::ostringstream& o, const b2z_circuit::Step& s) {
+    size_t nf = expr.size();
     switch (s.op) {
       case OP_CONST:
         is_ext.push_back(0);
-        o << "  const u32 f" << nf << " = " << fp_from_u32(s.a) << "u;\n";
-        nf++;
+        expr.push_back(std::to_string(fp_from_u32(s.a)) + "u");
         break;
       case OP_CONST_EXT:
         is_ext.push_back(1);
-        o << "  const E e" << nf << " = emake(" << fp_from_u32(s.a) << "u, " << fp_from_u32(s.b) << "u, " << fp_from_u32(s.c) << "u, "
-          << fp_from_u32(s.d) << "u);\n";
-        nf++;
+        expr.push_back("emake(" + std::to_string(fp_from_u32(s.a)) + "u, " + std::to_string(fp_from_u32(s.b)) + "u, " +
+                       std::to_string(fp_from_u32(s.c)) + "u, " + std::to_string(fp_from_u32(s.d)) + "u)");
         break;
       case OP_GET: {
         is_ext.push_back(0);
         uint32_t g = c->tap_group[s.a], col = c->tap_offset[s.a], back = c->tap_back[s.a];
         unsigned stride = trace_domain ? 1 : 4;
-        o << "  const u32 f" << nf << " = __ldg(g" << g << " + " << col << "ull * domain + ((i - " << (back * stride) << "ull) & mask));\n";
-        nf++;
+        (void)stride;
+        expr.push_back("ldc(cp.g" + std::to_string(g) + "[" + std::to_string(col) + "], ib" + std::to_string(back) + ")");
+        if (back > max_back) max_back = back;
       } break;
       case OP_GET_GLOBAL:
         is_ext.push_back(0);
-        o << "  const u32 f" << nf << " = __ldg(" << (s.a == 0 ? "globals" : "mixg") << " + " << s.b << ");\n";
-        nf++;
+        expr.push_back(std::string("ldv(") + (s.a == 0 ? "globals" : "mixg") + " + " + std::to_string(s.b) + ")");
         break;
       case OP_ADD: case OP_SUB: case OP_MUL: {
         bool ea = is_ext[s.a], eb = is_ext[s.b];
+        std::string A = operand(s.a), Bn = operand(s.b), e;
+        if (!ea && !eb) e = std::string(s.op == OP_ADD ? "fadd" : s.op == OP_SUB ? "fsub" : "fmul") + "(" + A + ", " + Bn + ")";
+        else if (ea && eb) e = std::string(s.op == OP_ADD ? "eadd" : s.op == OP_SUB ? "esub" : "emul") + "(" + A + ", " + Bn + ")";
+        else if (ea && !eb) e = std::string(s.op == OP_ADD ? "eaddf" : s.op == OP_SUB ? "esubf" : "emulf") + "(" + A + ", " + Bn + ")";
+        else e = s.op == OP_ADD ? "eaddf(" + Bn + ", " + A + ")" : s.op == OP_SUB ? "fsube(" + A + ", " + Bn + ")" : "emulf(" + Bn + ", " + A + ")";
         is_ext.push_back(ea | eb);
-        std::string A = nm(s.a), Bn = nm(s.b);
-        std::string expr;
-        if (!ea && !eb) expr = std::string(s.op == OP_ADD ? "fadd" : s.op == OP_SUB ? "fsub" : "fmul") + "(" + A + ", " + Bn + ")";
-        else if (ea && eb) expr = std::string(s.op == OP_ADD ? "eadd" : s.op == OP_SUB ? "esub" : "emul") + "(" + A + ", " + Bn + ")";
-        else if (ea && !eb) expr = std::string(s.op == OP_ADD ? "eaddf" : s.op == OP_SUB ? "esubf" : "emulf") + "(" + A + ", " + Bn + ")";
-        else expr = s.op == OP_ADD ? "eaddf(" + Bn + ", " + A + ")" : s.op == OP_SUB ? "fsube(" + A + ", " + Bn + ")" : "emulf(" + Bn + ", " + A + ")";
-        o << "  const " << ((ea | eb) ? "E e" : "u32 f") << nf << " = " << expr << ";\n";
-        nf++;
+        std::string name = std::string((ea | eb) ? "e" : "f") + std::to_string(nf);
+        o << "  const " << ((ea | eb) ? "E " : "u32 ") << name << " = " << e << ";\n";
+        expr.push_back(name);
       } break;
       default: break;
     }
   }
-  if (is_ext_out) *is_ext_out = is_ext;
-}
+};
 
 void circuit_codegen(b2z_circuit* c) {
   std::ostringstream o;
@@ -268,15 +281,20 @@ void circuit_codegen(b2z_circuit* c) {
   o << "// circuit \"" << std::string((const char*)c->info, 16) << "\": " << c->steps.size() << " constraint steps, " << c->n_taps
     << " taps\n";
   // ---- eval_check: one thread per point of the 4N coset ----
-  o << "extern \"C\" __global__ void __launch_bounds__(256) b2z_eval_check(u32* __restrict__ check, const u32* __restrict__ g0, "
-       "const u32* __restrict__ g1, const u32* __restrict__ g2, const u32* __restrict__ globals, const u32* __restrict__ mixg, "
+  // column base pointers travel as one by-value kernel parameter (constant bank => uniform registers, no per-load
+  // 64-bit multiply); rows are addressed with 32-bit byte offsets ib<back> = ((i - 4*back) & mask) * 4
+  o << "struct ColPtrs { const u32* g0[" << (c->group_size[0] ? c->group_size[0] : 1) << "]; const u32* g1["
+    << (c->group_size[1] ? c->group_size[1] : 1) << "]; const u32* g2[" << (c->group_size[2] ? c->group_size[2] : 1) << "]; };\n";
+  unsigned max_back = 0;
+  for (size_t t = 0; t < c->n_taps; t++) max_back = std::max(max_back, c->tap_back[t]);
+  o << "extern \"C\" __global__ void __launch_bounds__(128, 4) b2z_eval_check(u32* __restrict__ check, const __grid_constant__ ColPtrs cp, "
+       "const u32* __restrict__ globals, const u32* __restrict__ mixg, "
        "const u32* __restrict__ pm, u32 iz0, u32 iz1, u32 iz2, u32 iz3, u64 mask) {\n";
   o << "  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;\n  if (i > mask) return;\n  const u64 domain = mask + 1;\n";
+  for (unsigned b = 0; b <= max_back; b++) o << "  const u32 ib" << b << " = (u32)((i - " << 4 * b << "ull) & mask) << 2;\n";
   {
-    // interleave fp and mix steps in program order
-    std::vector<uint8_t> is_ext;
-    size_t nf = 0, nmx = 0;
-    auto nm = [&](size_t v) { return std::string(is_ext[v] ? "e" : "f") + std::to_string(v); };
+    Emitter em{c, false, {}, {}};
+    size_t nmx = 0;
     for (const auto& s : c->steps) {
       switch (s.op) {
         case OP_TRUE:
@@ -285,66 +303,35 @@ void circuit_codegen(b2z_circuit* c) {
           break;
         case OP_AND_EQZ: {
           std::string pw = "eld(pm + " + std::to_string(4 * c->mix_exp[s.a]) + ")";
-          std::string term = is_ext[s.b] ? "emul(" + pw + ", " + nm(s.b) + ")" : "emulf(" + pw + ", " + nm(s.b) + ")";
+          std::string term = em.is_ext[s.b] ? "emul(" + pw + ", " + em.operand(s.b) + ")" : "emulf(" + pw + ", " + em.operand(s.b) + ")";
           o << "  const E m" << nmx << " = eadd(m" << s.a << ", " << term << ");\n";
           nmx++;
         } break;
         case OP_AND_COND: {
           std::string pw = "eld(pm + " + std::to_string(4 * c->mix_exp[s.a]) + ")";
-          std::string inner = is_ext[s.b] ? "emul(m" + std::to_string(s.c) + ", " + nm(s.b) + ")" : "emulf(m" + std::to_string(s.c) + ", " + nm(s.b) + ")";
+          std::string inner = em.is_ext[s.b] ? "emul(m" + std::to_string(s.c) + ", " + em.operand(s.b) + ")"
+                                             : "emulf(m" + std::to_string(s.c) + ", " + em.operand(s.b) + ")";
           o << "  const E m" << nmx << " = eadd(m" << s.a << ", emul(" << inner << ", " << pw << "));\n";
           nmx++;
         } break;
-        default: {
-          std::vector<b2z_circuit::Step> one{s};
-          // emit a single fp step with correct numbering: reuse emit logic inline
-          switch (s.op) {
-            case OP_CONST:
-              is_ext.push_back(0);
-              o << "  const u32 f" << nf << " = " << fp_from_u32(s.a) << "u;\n";
-              break;
-            case OP_CONST_EXT:
-              is_ext.push_back(1);
-              o << "  const E e" << nf << " = emake(" << fp_from_u32(s.a) << "u, " << fp_from_u32(s.b) << "u, " << fp_from_u32(s.c)
-                << "u, " << fp_from_u32(s.d) << "u);\n";
-              break;
-            case OP_GET: {
-              is_ext.push_back(0);
-              uint32_t g = c->tap_group[s.a], col = c->tap_offset[s.a], back = c->tap_back[s.a];
-              o << "  const u32 f" << nf << " = __ldg(g" << g << " + " << col << "ull * domain + ((i - " << (back * 4) << "ull) & mask));\n";
-            } break;
-            case OP_GET_GLOBAL:
-              is_ext.push_back(0);
-              o << "  const u32 f" << nf << " = __ldg(" << (s.a == 0 ? "globals" : "mixg") << " + " << s.b << ");\n";
-              break;
-            default: {
-              bool ea = is_ext[s.a], eb = is_ext[s.b];
-              std::string A = nm(s.a), Bn = nm(s.b), expr;
-              if (!ea && !eb) expr = std::string(s.op == OP_ADD ? "fadd" : s.op == OP_SUB ? "fsub" : "fmul") + "(" + A + ", " + Bn + ")";
-              else if (ea && eb) expr = std::string(s.op == OP_ADD ? "eadd" : s.op == OP_SUB ? "esub" : "emul") + "(" + A + ", " + Bn + ")";
-              else if (ea && !eb) expr = std::string(s.op == OP_ADD ? "eaddf" : s.op == OP_SUB ? "esubf" : "emulf") + "(" + A + ", " + Bn + ")";
-              else expr = s.op == OP_ADD ? "eaddf(" + Bn + ", " + A + ")" : s.op == OP_SUB ? "fsube(" + A + ", " + Bn + ")" : "emulf(" + Bn + ", " + A + ")";
-              is_ext.push_back(ea | eb);
-              o << "  const " << ((ea | eb) ? "E e" : "u32 f") << nf << " = " << expr << ";\n";
-            } break;
-          }
-          nf++;
-        } break;
+        default: em.step(o, s); break;
       }
     }
   }
-  o << "  const u32 izs[4] = {iz0, iz1, iz2, iz3};\n";
-  o << "  const E r = emulf(m" << c->ret << ", izs[i & 3]);\n";
+  o << "  const u32 iz = (i & 2) ? ((i & 1) ? iz3 : iz2) : ((i & 1) ? iz1 : iz0);\n";
+  o << "  const E r = emulf(m" << c->ret << ", iz);\n";
   o << "  check[i] = r.a; check[domain + i] = r.b; check[2 * domain + i] = r.c; check[3 * domain + i] = r.d;\n}\n\n";
   // ---- witgen: one thread per active trace row; taps read the trace domain (stride 1) ----
-  o << "extern \"C\" __global__ void __launch_bounds__(256) b2z_witgen(u32* __restrict__ g2w, const u32* __restrict__ g1, "
+  o << "extern \"C\" __global__ void __launch_bounds__(256) b2z_witgen(const __grid_constant__ ColPtrs cp, "
        "const u32* __restrict__ globals, u64 mask, u64 active_rows) {\n";
-  o << "  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;\n  if (i >= active_rows) return;\n  const u64 domain = mask + 1;\n";
-  o << "  const u32* g2 = g2w; const u32* g0 = 0; const u32* mixg = 0; (void)g0; (void)mixg;\n";
-  std::vector<uint8_t> wext;
-  emit_fp_steps(o, c->wit_steps, c, true, &wext);
-  for (size_t k = 0; k < c->wit_store_col.size(); k++)
-    o << "  g2w[" << c->wit_store_col[k] << "ull * domain + i] = f" << c->wit_store_var[k] << ";\n";
+  o << "  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;\n  if (i >= active_rows) return;\n";
+  for (unsigned b = 0; b <= max_back; b++) o << "  const u32 ib" << b << " = (u32)((i - " << b << "ull) & mask) << 2;\n";
+  {
+    Emitter em{c, true, {}, {}};
+    for (const auto& s : c->wit_steps) em.step(o, s);
+    for (size_t k = 0; k < c->wit_store_col.size(); k++)
+      o << "  const_cast<u32*>(cp.g2[" << c->wit_store_col[k] << "])[i] = " << em.operand(c->wit_store_var[k]) << ";\n";
+  }
   o << "}\n";
   c->source = o.str();
   uint64_t h = 1469598103934665603ull;

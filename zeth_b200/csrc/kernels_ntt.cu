@@ -216,21 +216,44 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(PassArgs a) {
   }
   const size_t twist_mask = ((size_t)1 << (a.s_lo + R)) - 1;
 
-  // ---- load (forward: inter-pass twist applied here) ----
+  // ---- load (forward: inter-pass twist applied here); 8 independent loads in flight per thread ----
+  constexpr unsigned U = 8;
   if (rows_mode) {
-    for (unsigned e = threadIdx.x; e < tile_elems; e += blockDim.x) {
-      size_t g = base + e;
-      uint32_t x = 0;
-      if (g < a.total) x = a.ebits ? __ldg(a.in + (g >> a.ebits)) : a.in[g];
-      sm[(e >> R) * pitch_l + (e & (npts - 1))] = x;
+    for (unsigned e0 = threadIdx.x; e0 < tile_elems; e0 += U * blockDim.x) {
+      uint32_t x[U];
+#pragma unroll
+      for (unsigned u = 0; u < U; u++) {
+        unsigned e = e0 + u * blockDim.x;
+        size_t g = base + e;
+        x[u] = 0;
+        if (e < tile_elems && g < a.total) x[u] = a.ebits ? __ldg(a.in + (g >> a.ebits)) : a.in[g];
+      }
+#pragma unroll
+      for (unsigned u = 0; u < U; u++) {
+        unsigned e = e0 + u * blockDim.x;
+        if (e < tile_elems) sm[(e >> R) * pitch_l + (e & (npts - 1))] = x[u];
+      }
     }
   } else {
-    for (unsigned e = threadIdx.x; e < tile_elems; e += blockDim.x) {
-      unsigned p = e >> 5, l = e & 31;
-      size_t g = base + ((size_t)p << a.s_lo) + l;
-      uint32_t x = a.in[g];
-      if (!INV && a.pass_twist) x = fp_mul(x, __ldg(a.pass_twist + (g & twist_mask)));
-      sm[p * 32 + l] = x;
+    for (unsigned e0 = threadIdx.x; e0 < tile_elems; e0 += U * blockDim.x) {
+      uint32_t x[U], tw[U];
+#pragma unroll
+      for (unsigned u = 0; u < U; u++) {
+        unsigned e = e0 + u * blockDim.x;
+        unsigned p = e >> 5, l = e & 31;
+        size_t g = base + ((size_t)p << a.s_lo) + l;
+        x[u] = 0;
+        tw[u] = 0;
+        if (e < tile_elems) {
+          x[u] = a.in[g];
+          if (!INV && a.pass_twist) tw[u] = __ldg(a.pass_twist + (g & twist_mask));
+        }
+      }
+#pragma unroll
+      for (unsigned u = 0; u < U; u++) {
+        unsigned e = e0 + u * blockDim.x;
+        if (e < tile_elems) sm[e] = (!INV && a.pass_twist) ? fp_mul(x[u], tw[u]) : x[u];
+      }
     }
   }
   __syncthreads();
@@ -254,23 +277,49 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(PassArgs a) {
 
   // ---- store (inverse: inter-pass twist / final scale applied here) ----
   if (rows_mode) {
-    for (unsigned e = threadIdx.x; e < tile_elems; e += blockDim.x) {
-      size_t g = base + e;
-      if (g >= a.total) continue;
-      uint32_t x = sm[(e >> R) * pitch_l + (e & (npts - 1))];
-      if (a.apply_scale) {
-        x = fp_mul(x, a.scale);
-        if (a.scale_tab) x = fp_mul(x, __ldg(a.scale_tab + (g & (((size_t)1 << a.logn) - 1))));
+    for (unsigned e0 = threadIdx.x; e0 < tile_elems; e0 += U * blockDim.x) {
+      uint32_t tw[U];
+#pragma unroll
+      for (unsigned u = 0; u < U; u++) {
+        unsigned e = e0 + u * blockDim.x;
+        size_t g = base + e;
+        tw[u] = 0;
+        if (a.apply_scale && a.scale_tab && e < tile_elems && g < a.total) tw[u] = __ldg(a.scale_tab + (g & (((size_t)1 << a.logn) - 1)));
       }
-      a.out[g] = x;
+#pragma unroll
+      for (unsigned u = 0; u < U; u++) {
+        unsigned e = e0 + u * blockDim.x;
+        size_t g = base + e;
+        if (e >= tile_elems || g >= a.total) continue;
+        uint32_t x = sm[(e >> R) * pitch_l + (e & (npts - 1))];
+        if (a.apply_scale) {
+          x = fp_mul(x, a.scale);
+          if (a.scale_tab) x = fp_mul(x, tw[u]);
+        }
+        a.out[g] = x;
+      }
     }
   } else {
-    for (unsigned e = threadIdx.x; e < tile_elems; e += blockDim.x) {
-      unsigned p = e >> 5, l = e & 31;
-      size_t g = base + ((size_t)p << a.s_lo) + l;
-      uint32_t x = sm[p * 32 + l];
-      if (INV && a.pass_twist) x = fp_mul(x, __ldg(a.pass_twist + (g & twist_mask)));
-      a.out[g] = x;
+    for (unsigned e0 = threadIdx.x; e0 < tile_elems; e0 += U * blockDim.x) {
+      uint32_t tw[U];
+#pragma unroll
+      for (unsigned u = 0; u < U; u++) {
+        unsigned e = e0 + u * blockDim.x;
+        unsigned p = e >> 5, l = e & 31;
+        size_t g = base + ((size_t)p << a.s_lo) + l;
+        tw[u] = 0;
+        if (INV && a.pass_twist && e < tile_elems) tw[u] = __ldg(a.pass_twist + (g & twist_mask));
+      }
+#pragma unroll
+      for (unsigned u = 0; u < U; u++) {
+        unsigned e = e0 + u * blockDim.x;
+        if (e >= tile_elems) continue;
+        unsigned p = e >> 5, l = e & 31;
+        size_t g = base + ((size_t)p << a.s_lo) + l;
+        uint32_t x = sm[e];
+        if (INV && a.pass_twist) x = fp_mul(x, tw[u]);
+        a.out[g] = x;
+      }
     }
   }
 }
@@ -295,9 +344,9 @@ static void plan_passes(unsigned logn, unsigned* R, unsigned* np) {
 }
 
 static size_t chunk_columns(size_t count, unsigned logn) {
-  // keep one chunk's working set (in place: 4 B * cols * n) around 40 MB so the later passes hit in the 126 MB L2
+  // keep one chunk's working set (in place: 4 B * cols * n) around 64 MB so the later passes hit in the 126 MB L2
   size_t bytes_per_col = (size_t)4 << logn;
-  size_t c = (40u << 20) / bytes_per_col;
+  size_t c = (64u << 20) / bytes_per_col;
   if (c < 1) c = 1;
   return c < count ? c : count;
 }
