@@ -136,46 +136,35 @@ __device__ __forceinline__ void dif_base(uint32_t* v) {
   }
 }
 
-// One radix group over bits [g_lo, g_lo + Q) of the R-bit point index, for all lanes of the tile.
-//   smem address of (point p, lane l) = p * pitch_p + l * pitch_l
-//   pre/post twist (intra-pass, warp-uniform): multiply point p by twist[p] after (forward) / before (inverse) the group
-template <int Q, bool INV, int FIRST>
-__device__ __forceinline__ void radix_group(uint32_t* sm, unsigned R, unsigned g_lo, unsigned pitch_p, unsigned pitch_l,
-                                            const uint32_t* __restrict__ twist, unsigned lane, unsigned warp, unsigned nwarps) {
-  const unsigned sets = 1u << (R - Q);
-  for (unsigned set = warp; set < sets; set += nwarps) {
-    // set index -> the point bits outside [g_lo, g_lo+Q)
-    unsigned low = set & ((1u << g_lo) - 1), high = set >> g_lo;
-    unsigned p0 = (high << (g_lo + Q)) | low;
+// One radix group over bits [G_LO, G_LO + Q) of the R-bit point index, for all lanes of the tile.
+//   smem address of (point p, lane l) = p * PITCH_P + l * PITCH_L  (all compile-time, so every access is base + immediate)
+//   intra-pass twist (warp-uniform, staged in shared memory): multiply point p by tws[p] after (forward) / before (inverse)
+template <int R, int Q, int G_LO, bool ROWS, bool INV, int FIRST, bool TWIST>
+__device__ __forceinline__ void radix_group(uint32_t* sm, const uint32_t* tws, unsigned lane, unsigned warp, unsigned nwarps) {
+  constexpr unsigned PITCH_P = ROWS ? 1u : 32u;
+  constexpr unsigned PITCH_L = ROWS ? ((1u << R) + 1u) : 1u;
+  constexpr unsigned SETS = 1u << (R - Q);
+  uint32_t* lane_base = sm + lane * PITCH_L;
+  for (unsigned set = warp; set < SETS; set += nwarps) {
+    // set index -> the point bits outside [G_LO, G_LO+Q)
+    const unsigned low = set & ((1u << G_LO) - 1), high = set >> G_LO;
+    const unsigned p0 = (high << (G_LO + Q)) | low;
+    uint32_t* base = lane_base + p0 * PITCH_P;
     uint32_t v[1 << Q];
 #pragma unroll
     for (int j = 0; j < (1 << Q); j++) {
-      unsigned p = p0 | ((unsigned)j << g_lo);
-      uint32_t x = sm[p * pitch_p + lane * pitch_l];
-      if (INV && twist) x = fp_mul(x, __ldg(twist + p));
+      uint32_t x = base[(j << G_LO) * PITCH_P];
+      if (INV && TWIST) x = fp_mul(x, tws[p0 + (j << G_LO)]);
       v[j] = x;
     }
     if (INV) dif_base<Q>(v);
     else dit_base<Q, FIRST>(v);
 #pragma unroll
     for (int j = 0; j < (1 << Q); j++) {
-      unsigned p = p0 | ((unsigned)j << g_lo);
       uint32_t x = v[j];
-      if (!INV && twist) x = fp_mul(x, __ldg(twist + p));
-      sm[p * pitch_p + lane * pitch_l] = x;
+      if (!INV && TWIST) x = fp_mul(x, tws[p0 + (j << G_LO)]);
+      base[(j << G_LO) * PITCH_P] = x;
     }
-  }
-}
-
-template <bool INV, int FIRST>
-__device__ __forceinline__ void radix_dispatch(unsigned Q, uint32_t* sm, unsigned R, unsigned g_lo, unsigned pitch_p, unsigned pitch_l,
-                                               const uint32_t* twist, unsigned lane, unsigned warp, unsigned nwarps) {
-  switch (Q) {
-    case 4: radix_group<4, INV, FIRST>(sm, R, g_lo, pitch_p, pitch_l, twist, lane, warp, nwarps); break;
-    case 3: radix_group<3, INV, FIRST>(sm, R, g_lo, pitch_p, pitch_l, twist, lane, warp, nwarps); break;
-    case 2: radix_group<2, INV, FIRST>(sm, R, g_lo, pitch_p, pitch_l, twist, lane, warp, nwarps); break;
-    case 1: radix_group<1, INV, FIRST>(sm, R, g_lo, pitch_p, pitch_l, twist, lane, warp, nwarps); break;
-    default: break;
   }
 }
 
@@ -187,111 +176,119 @@ struct PassArgs {
   const uint32_t* scale_tab;    // optional per-position factor on the final inverse store (zk_shift), period 2^logn
   uint32_t scale;               // final inverse scale (1/n), applied when apply_scale
   unsigned logn;                // per-column transform size
-  unsigned s_lo, R, q1;         // bits below this pass, bits of this pass, size of the first radix group
+  unsigned s_lo;                // bits below this pass
   unsigned ebits;               // expand bits folded into the first forward pass's loads
   int apply_scale;
   size_t total;                 // total elements of the launch (columns * n)
 };
 
-// rows mode (s_lo == 0): tile = 32 consecutive rows of 2^R contiguous points, lane = row, pitch (2^R + 1)
-// strided mode          : tile = 2^R points at stride 2^s_lo x 32 adjacent positions, lane = position, pitch_p = 32
-template <bool INV, int FIRST>
+// ROWS (s_lo == 0): tile = 32 consecutive rows of 2^R contiguous points, lane = row, pitch (2^R + 1)
+// strided         : tile = 2^R points at stride 2^s_lo x 32 adjacent positions, lane = position, pitch_p = 32
+template <bool INV, int FIRST, int R, bool ROWS>
 __global__ void __launch_bounds__(256) ntt_pass_kernel(PassArgs a) {
+  constexpr int Q1 = R < 4 ? R : 4;
+  constexpr int Q2 = R - Q1;
+  constexpr unsigned NPTS = 1u << R;
+  constexpr unsigned PITCH_L = ROWS ? (NPTS + 1u) : 1u;
+  constexpr unsigned TILE = NPTS * 32u;
+  constexpr unsigned U = 8;
   extern __shared__ uint32_t sm[];
-  const unsigned R = a.R, npts = 1u << R;
+  uint32_t* tws = sm + (ROWS ? 32u * (NPTS + 1u) : TILE);  // intra-pass twist table (NPTS words)
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const bool rows_mode = (a.s_lo == 0);
-  const unsigned pitch_p = rows_mode ? 1u : 32u;
-  const unsigned pitch_l = rows_mode ? (npts + 1) : 1u;
-  const size_t tile_elems = (size_t)npts * 32;
-  size_t base;       // global index of (point 0, lane 0)
-  if (rows_mode) {
-    base = (size_t)blockIdx.x * tile_elems;
+  size_t base;  // global index of (point 0, lane 0)
+  if (ROWS) {
+    base = (size_t)blockIdx.x * TILE;
   } else {
-    // tiles enumerate (hi, lo_blk): hi over total / 2^(s_lo+R), lo_blk over 2^s_lo / 32
     const unsigned lo_blocks_log = a.s_lo - 5;
     size_t hi = (size_t)blockIdx.x >> lo_blocks_log;
     size_t lo_blk = (size_t)blockIdx.x & (((size_t)1 << lo_blocks_log) - 1);
     base = (hi << (a.s_lo + R)) | (lo_blk << 5);
   }
-  const size_t twist_mask = ((size_t)1 << (a.s_lo + R)) - 1;
+  const uint32_t twist_mask32 = (uint32_t)((((size_t)1 << (a.s_lo + R)) - 1));
+  if (Q2 > 0) {
+    for (unsigned p = threadIdx.x; p < NPTS; p += blockDim.x) tws[p] = a.group_twist[p];
+  }
 
-  // ---- load (forward: inter-pass twist applied here); 8 independent loads in flight per thread ----
-  constexpr unsigned U = 8;
-  if (rows_mode) {
-    for (unsigned e0 = threadIdx.x; e0 < tile_elems; e0 += U * blockDim.x) {
+  // ---- load (forward: inter-pass twist applied here); U independent loads in flight per thread ----
+  if (ROWS) {
+#pragma unroll 1
+    for (unsigned e0 = threadIdx.x; e0 < TILE; e0 += U * 256) {
       uint32_t x[U];
 #pragma unroll
       for (unsigned u = 0; u < U; u++) {
-        unsigned e = e0 + u * blockDim.x;
+        unsigned e = e0 + u * 256;
         size_t g = base + e;
         x[u] = 0;
-        if (e < tile_elems && g < a.total) x[u] = a.ebits ? __ldg(a.in + (g >> a.ebits)) : a.in[g];
+        if (e < TILE && g < a.total) x[u] = a.ebits ? __ldg(a.in + (g >> a.ebits)) : a.in[g];
       }
 #pragma unroll
       for (unsigned u = 0; u < U; u++) {
-        unsigned e = e0 + u * blockDim.x;
-        if (e < tile_elems) sm[(e >> R) * pitch_l + (e & (npts - 1))] = x[u];
+        unsigned e = e0 + u * 256;
+        if (e < TILE) sm[(e >> R) * PITCH_L + (e & (NPTS - 1))] = x[u];
       }
     }
   } else {
-    for (unsigned e0 = threadIdx.x; e0 < tile_elems; e0 += U * blockDim.x) {
+    const uint32_t* src = a.in + base;
+    const uint32_t tbase = (uint32_t)base & twist_mask32;
+#pragma unroll 1
+    for (unsigned e0 = threadIdx.x; e0 < TILE; e0 += U * 256) {
       uint32_t x[U], tw[U];
 #pragma unroll
       for (unsigned u = 0; u < U; u++) {
-        unsigned e = e0 + u * blockDim.x;
+        unsigned e = e0 + u * 256;
         unsigned p = e >> 5, l = e & 31;
-        size_t g = base + ((size_t)p << a.s_lo) + l;
         x[u] = 0;
         tw[u] = 0;
-        if (e < tile_elems) {
-          x[u] = a.in[g];
-          if (!INV && a.pass_twist) tw[u] = __ldg(a.pass_twist + (g & twist_mask));
+        if (e < TILE) {
+          size_t off = ((size_t)p << a.s_lo) + l;
+          x[u] = src[off];
+          if (!INV && a.pass_twist) tw[u] = __ldg(a.pass_twist + ((tbase + (uint32_t)off) & twist_mask32));
         }
       }
 #pragma unroll
       for (unsigned u = 0; u < U; u++) {
-        unsigned e = e0 + u * blockDim.x;
-        if (e < tile_elems) sm[e] = (!INV && a.pass_twist) ? fp_mul(x[u], tw[u]) : x[u];
+        unsigned e = e0 + u * 256;
+        if (e < TILE) sm[e] = (!INV && a.pass_twist) ? fp_mul(x[u], tw[u]) : x[u];
       }
     }
   }
   __syncthreads();
 
   // ---- compute: at most two radix groups (R <= 8) ----
-  const unsigned q1 = a.q1, q2 = R - q1;
   if (!INV) {
-    radix_dispatch<false, FIRST>(q1, sm, R, 0, pitch_p, pitch_l, q2 ? a.group_twist : nullptr, lane, warp, nwarps);
-    if (q2) {
+    radix_group<R, Q1, 0, ROWS, false, FIRST, (Q2 > 0)>(sm, tws, lane, warp, nwarps);
+    if (Q2 > 0) {
       __syncthreads();
-      radix_dispatch<false, 1>(q2, sm, R, q1, pitch_p, pitch_l, nullptr, lane, warp, nwarps);
+      radix_group<R, (Q2 > 0 ? Q2 : 1), Q1, ROWS, false, 1, false>(sm, tws, lane, warp, nwarps);
     }
   } else {
-    if (q2) {
-      radix_dispatch<true, 1>(q2, sm, R, q1, pitch_p, pitch_l, nullptr, lane, warp, nwarps);
+    if (Q2 > 0) {
+      radix_group<R, (Q2 > 0 ? Q2 : 1), Q1, ROWS, true, 1, false>(sm, tws, lane, warp, nwarps);
       __syncthreads();
     }
-    radix_dispatch<true, 1>(q1, sm, R, 0, pitch_p, pitch_l, q2 ? a.group_twist : nullptr, lane, warp, nwarps);
+    radix_group<R, Q1, 0, ROWS, true, 1, (Q2 > 0)>(sm, tws, lane, warp, nwarps);
   }
   __syncthreads();
 
   // ---- store (inverse: inter-pass twist / final scale applied here) ----
-  if (rows_mode) {
-    for (unsigned e0 = threadIdx.x; e0 < tile_elems; e0 += U * blockDim.x) {
+  if (ROWS) {
+    const uint32_t nmask = (uint32_t)(((size_t)1 << a.logn) - 1);
+#pragma unroll 1
+    for (unsigned e0 = threadIdx.x; e0 < TILE; e0 += U * 256) {
       uint32_t tw[U];
 #pragma unroll
       for (unsigned u = 0; u < U; u++) {
-        unsigned e = e0 + u * blockDim.x;
+        unsigned e = e0 + u * 256;
         size_t g = base + e;
         tw[u] = 0;
-        if (a.apply_scale && a.scale_tab && e < tile_elems && g < a.total) tw[u] = __ldg(a.scale_tab + (g & (((size_t)1 << a.logn) - 1)));
+        if (a.apply_scale && a.scale_tab && e < TILE && g < a.total) tw[u] = __ldg(a.scale_tab + ((uint32_t)g & nmask));
       }
 #pragma unroll
       for (unsigned u = 0; u < U; u++) {
-        unsigned e = e0 + u * blockDim.x;
+        unsigned e = e0 + u * 256;
         size_t g = base + e;
-        if (e >= tile_elems || g >= a.total) continue;
-        uint32_t x = sm[(e >> R) * pitch_l + (e & (npts - 1))];
+        if (e >= TILE || g >= a.total) continue;
+        uint32_t x = sm[(e >> R) * PITCH_L + (e & (NPTS - 1))];
         if (a.apply_scale) {
           x = fp_mul(x, a.scale);
           if (a.scale_tab) x = fp_mul(x, tw[u]);
@@ -300,25 +297,26 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(PassArgs a) {
       }
     }
   } else {
-    for (unsigned e0 = threadIdx.x; e0 < tile_elems; e0 += U * blockDim.x) {
+    uint32_t* dst = a.out + base;
+    const uint32_t tbase = (uint32_t)base & twist_mask32;
+#pragma unroll 1
+    for (unsigned e0 = threadIdx.x; e0 < TILE; e0 += U * 256) {
       uint32_t tw[U];
 #pragma unroll
       for (unsigned u = 0; u < U; u++) {
-        unsigned e = e0 + u * blockDim.x;
+        unsigned e = e0 + u * 256;
         unsigned p = e >> 5, l = e & 31;
-        size_t g = base + ((size_t)p << a.s_lo) + l;
         tw[u] = 0;
-        if (INV && a.pass_twist && e < tile_elems) tw[u] = __ldg(a.pass_twist + (g & twist_mask));
+        if (INV && a.pass_twist && e < TILE) tw[u] = __ldg(a.pass_twist + ((tbase + (uint32_t)(((size_t)p << a.s_lo) + l)) & twist_mask32));
       }
 #pragma unroll
       for (unsigned u = 0; u < U; u++) {
-        unsigned e = e0 + u * blockDim.x;
-        if (e >= tile_elems) continue;
+        unsigned e = e0 + u * 256;
+        if (e >= TILE) continue;
         unsigned p = e >> 5, l = e & 31;
-        size_t g = base + ((size_t)p << a.s_lo) + l;
         uint32_t x = sm[e];
         if (INV && a.pass_twist) x = fp_mul(x, tw[u]);
-        a.out[g] = x;
+        dst[((size_t)p << a.s_lo) + l] = x;
       }
     }
   }
@@ -351,18 +349,29 @@ static size_t chunk_columns(size_t count, unsigned logn) {
   return c < count ? c : count;
 }
 
-template <bool INV, int FIRST>
-static b2z_err launch_one(b2z_ctx* ctx, const PassArgs& a) {
-  const unsigned npts = 1u << a.R;
-  size_t smem = a.s_lo == 0 ? sizeof(uint32_t) * 32 * (npts + 1) : sizeof(uint32_t) * 32 * npts;
-  size_t tile_elems = (size_t)npts * 32;
+template <bool INV, int FIRST, int R, bool ROWS>
+static b2z_err launch_inst(b2z_ctx* ctx, const PassArgs& a) {
+  constexpr unsigned NPTS = 1u << R;
+  size_t smem = sizeof(uint32_t) * ((ROWS ? 32 * (NPTS + 1) : 32 * NPTS) + NPTS);
+  size_t tile_elems = (size_t)NPTS * 32;
   size_t tiles = (a.total + tile_elems - 1) / tile_elems;
-  if (a.s_lo != 0) B2Z_REQUIRE(a.total % tile_elems == 0, "strided NTT pass needs whole tiles");
-  unsigned threads = 256;
-  ntt_pass_kernel<INV, FIRST><<<(unsigned)tiles, threads, smem, ctx->stream>>>(a);
+  if (!ROWS) B2Z_REQUIRE(a.total % tile_elems == 0, "strided NTT pass needs whole tiles");
+  ntt_pass_kernel<INV, FIRST, R, ROWS><<<(unsigned)tiles, 256, smem, ctx->stream>>>(a);
   ctx->launches++;
   B2Z_CUDA(cudaGetLastError());
   return nullptr;
+}
+template <bool INV, int FIRST>
+static b2z_err launch_one(b2z_ctx* ctx, const PassArgs& a, unsigned R) {
+  const bool rows = (a.s_lo == 0);
+#define B2Z_NTT_CASE(RR)                                                         \
+  case RR:                                                                       \
+    return rows ? launch_inst<INV, FIRST, RR, true>(ctx, a) : launch_inst<INV, 1, RR, false>(ctx, a);
+  switch (R) {
+    B2Z_NTT_CASE(1) B2Z_NTT_CASE(2) B2Z_NTT_CASE(3) B2Z_NTT_CASE(4) B2Z_NTT_CASE(5) B2Z_NTT_CASE(6) B2Z_NTT_CASE(7) B2Z_NTT_CASE(8)
+    default: return set_error("unsupported NTT pass width");
+  }
+#undef B2Z_NTT_CASE
 }
 
 // forward transform of `count` columns: out (2^logn per column) from in (2^(logn - ebits) per column when expanding)
@@ -377,7 +386,7 @@ b2z_err launch_evaluate(b2z_ctx* ctx, uint32_t* out, const uint32_t* in, size_t 
   }
   unsigned R[8], np = 0;
   plan_passes(logn, R, &np);
-  B2Z_REQUIRE(expand_bits <= (R[0] < 4 ? R[0] : 4), "expand_bits larger than the first radix group");
+  B2Z_REQUIRE(expand_bits <= 2 && expand_bits <= (R[0] < 4 ? R[0] : 4), "expand_bits larger than the first radix group");
   const uint32_t* pass_tw[8] = {};
   const uint32_t* grp_tw[8] = {};
   unsigned s_lo = 0;
@@ -402,18 +411,15 @@ b2z_err launch_evaluate(b2z_ctx* ctx, uint32_t* out, const uint32_t* in, size_t 
       a.scale = 0;
       a.logn = logn;
       a.s_lo = s_lo;
-      a.R = R[k];
-      a.q1 = R[k] < 4 ? R[k] : 4;
       a.ebits = (k == 0 && expanding) ? expand_bits : 0;
       a.apply_scale = 0;
       a.total = cols * n;
       unsigned first = (k == 0) ? expand_bits + 1 : 1;  // skipped layers are valid for in-place evaluate_ntt(expand_bits) too
       switch (first) {
-        case 1: B2Z_TRY((launch_one<false, 1>(ctx, a))); break;
-        case 2: B2Z_TRY((launch_one<false, 2>(ctx, a))); break;
-        case 3: B2Z_TRY((launch_one<false, 3>(ctx, a))); break;
-        case 4: B2Z_TRY((launch_one<false, 4>(ctx, a))); break;
-        default: B2Z_TRY((launch_one<false, 5>(ctx, a))); break;
+        case 1: B2Z_TRY((launch_one<false, 1>(ctx, a, R[k]))); break;
+        case 2: B2Z_TRY((launch_one<false, 2>(ctx, a, R[k]))); break;
+        case 3: B2Z_TRY((launch_one<false, 3>(ctx, a, R[k]))); break;
+        default: return set_error("expand_bits > 2 is not supported");
       }
       s_lo += R[k];
     }
@@ -454,12 +460,10 @@ b2z_err launch_interpolate(b2z_ctx* ctx, uint32_t* io, size_t count, unsigned po
       a.scale = norm;
       a.logn = logn;
       a.s_lo = s_los[kk];
-      a.R = R[kk];
-      a.q1 = R[kk] < 4 ? R[kk] : 4;
       a.ebits = 0;
       a.apply_scale = (kk == 0);
       a.total = cols * n;
-      B2Z_TRY((launch_one<true, 1>(ctx, a)));
+      B2Z_TRY((launch_one<true, 1>(ctx, a, R[kk])));
     }
   }
   return nullptr;
