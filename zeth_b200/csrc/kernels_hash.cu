@@ -34,13 +34,13 @@ __global__ void __launch_bounds__(128) hash_rows_kernel(uint32_t* __restrict__ o
   for (size_t blk = 0; blk < full; blk++) {
 #pragma unroll
     for (int i = 0; i < P2_RATE; i++) s[i] = __ldg(p + (blk * P2_RATE + i) * rows);
-    p2_permute(s, c_p2);
+    p2_permute_dev(s, c_p2);
   }
   size_t rem = cols - full * P2_RATE;
   if (rem != 0 || cols == 0) {
 #pragma unroll
     for (int i = 0; i < P2_RATE; i++) s[i] = (size_t)i < rem ? __ldg(p + (full * P2_RATE + i) * rows) : 0u;
-    p2_permute(s, c_p2);
+    p2_permute_dev(s, c_p2);
   }
   uint4* o = reinterpret_cast<uint4*>(out + 8 * r);
   o[0] = make_uint4(s[0], s[1], s[2], s[3]);
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(128) hash_fold_kernel(uint32_t* __restrict__ n
   const uint4* in = reinterpret_cast<const uint4*>(nodes + 8 * (in_size + 2 * j));
   uint4 a = in[0], b = in[1], c = in[2], d = in[3];
   uint32_t s[P2_CELLS] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w, 0, 0, 0, 0, 0, 0, 0, 0};
-  p2_permute(s, c_p2);
+  p2_permute_dev(s, c_p2);
   uint4* o = reinterpret_cast<uint4*>(nodes + 8 * (out_size + j));
   o[0] = make_uint4(s[0], s[1], s[2], s[3]);
   o[1] = make_uint4(s[4], s[5], s[6], s[7]);

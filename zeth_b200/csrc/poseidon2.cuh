@@ -18,8 +18,11 @@ constexpr int P2_ROUNDS_PARTIAL = 21;
 constexpr int P2_NUM_RC = 2 * P2_ROUNDS_HALF_FULL * P2_CELLS + P2_ROUNDS_PARTIAL;  // 213
 
 struct P2Consts {
-  uint32_t rc[P2_NUM_RC];   // Montgomery form
-  uint32_t diag[P2_CELLS];  // Montgomery form
+  uint32_t rc[P2_NUM_RC];          // Montgomery form
+  uint32_t diag[P2_CELLS];         // Montgomery form
+  int32_t rc_minus_p[P2_NUM_RC];   // rc - P as a signed value in (-P, 0]  (device s-box path)
+  uint32_t diag_canon[P2_CELLS];   // canonical D_i                        (device Shoup path)
+  uint32_t diag_shoup[P2_CELLS];   // floor(D_i * 2^32 / P)
 };
 
 const P2Consts& p2_host_consts();  // transcript.cpp
@@ -74,6 +77,60 @@ B2Z_HD void p2_m_int(uint32_t* s, const uint32_t* diag) {
 #pragma unroll
   for (int i = 0; i < P2_CELLS; i++) s[i] = fp_add(tot, fp_mul(diag[i], s[i]));
 }
+
+#if defined(__CUDACC__)
+// ---- device-tuned variants (same canonical results; see DESIGN.md "Poseidon2 instruction budget") ----
+// Signed-redundant Montgomery product: inputs in (-P, P) as int32, output in (-P, P); no final correction.
+__device__ __forceinline__ int32_t fp_mul_s(int32_t a, int32_t b) {
+  int64_t t = (int64_t)a * b;
+  uint32_t m = (uint32_t)t * MONT_PINV;
+  int32_t u = __mulhi((int32_t)m, (int32_t)P);
+  return (int32_t)(t >> 32) - u;
+}
+// x^7 of (s + rc): one raw add (rc - P keeps the sum inside (-P, P)), four uncorrected products, one final correction
+__device__ __forceinline__ uint32_t p2_sbox_rc(uint32_t s, int32_t rc_minus_p) {
+  int32_t x = (int32_t)s + rc_minus_p;
+  int32_t x2 = fp_mul_s(x, x);
+  int32_t x3 = fp_mul_s(x2, x);
+  int32_t x4 = fp_mul_s(x2, x2);
+  uint32_t x7 = (uint32_t)fp_mul_s(x3, x4);
+  return umin32(x7, x7 + P);
+}
+// Shoup product by a constant: x * d mod P with dp = floor(d * 2^32 / P); x canonical, result canonical
+__device__ __forceinline__ uint32_t fp_mul_shoup(uint32_t x, uint32_t d, uint32_t dp) {
+  uint32_t q = __umulhi(x, dp);
+  uint32_t r = x * d - q * P;
+  return umin32(r, r - P);
+}
+__device__ __forceinline__ void p2_m_int_dev(uint32_t* s, const P2Consts& k) {
+  uint32_t tot = 0;
+#pragma unroll
+  for (int i = 0; i < P2_CELLS; i++) tot = fp_add(tot, s[i]);
+#pragma unroll
+  for (int i = 0; i < P2_CELLS; i++) s[i] = fp_add(tot, fp_mul_shoup(s[i], k.diag_canon[i], k.diag_shoup[i]));
+}
+__device__ __forceinline__ void p2_permute_dev(uint32_t* s, const P2Consts& k) {
+  const int32_t* rc = k.rc_minus_p;
+  p2_m_ext(s);
+  for (int r = 0; r < P2_ROUNDS_HALF_FULL; r++) {
+#pragma unroll
+    for (int i = 0; i < P2_CELLS; i++) s[i] = p2_sbox_rc(s[i], rc[i]);
+    rc += P2_CELLS;
+    p2_m_ext(s);
+  }
+  for (int r = 0; r < P2_ROUNDS_PARTIAL; r++) {
+    s[0] = p2_sbox_rc(s[0], rc[0]);
+    rc += 1;
+    p2_m_int_dev(s, k);
+  }
+  for (int r = 0; r < P2_ROUNDS_HALF_FULL; r++) {
+#pragma unroll
+    for (int i = 0; i < P2_CELLS; i++) s[i] = p2_sbox_rc(s[i], rc[i]);
+    rc += P2_CELLS;
+    p2_m_ext(s);
+  }
+}
+#endif
 
 B2Z_HD void p2_permute(uint32_t* s, const P2Consts& k) {
   const uint32_t* rc = k.rc;

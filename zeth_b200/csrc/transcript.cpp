@@ -15,8 +15,16 @@ namespace b2z {
 const P2Consts& p2_host_consts() {
   static P2Consts k = [] {
     P2Consts c;
-    for (int i = 0; i < P2_NUM_RC; i++) c.rc[i] = fp_from_u32(P2_ROUND_CONSTANTS[i]);
-    for (int i = 0; i < P2_CELLS; i++) c.diag[i] = fp_from_u32(P2_M_INT_DIAG[i]);
+    for (int i = 0; i < P2_NUM_RC; i++) {
+      c.rc[i] = fp_from_u32(P2_ROUND_CONSTANTS[i]);
+      c.rc_minus_p[i] = (int32_t)(c.rc[i] - P);  // in (-P, 0] as a two's complement value (rc = 0 maps to -P + P... see below)
+      if (c.rc[i] == 0) c.rc_minus_p[i] = 0;
+    }
+    for (int i = 0; i < P2_CELLS; i++) {
+      c.diag[i] = fp_from_u32(P2_M_INT_DIAG[i]);
+      c.diag_canon[i] = P2_M_INT_DIAG[i];
+      c.diag_shoup[i] = (uint32_t)((((unsigned __int128)P2_M_INT_DIAG[i]) << 32) / P);
+    }
     return c;
   }();
   return k;
