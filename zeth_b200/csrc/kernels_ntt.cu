@@ -210,45 +210,55 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(PassArgs a) {
   }
 
   // ---- load (forward: inter-pass twist applied here); U independent loads in flight per thread ----
+  // element e = tid + 256*k of the tile: strided mode point p = (tid >> 5) + 8k, lane l = tid & 31;
+  // rows mode row = (tid >> R) + k * 2^(8-R), column = tid & (NPTS-1)   (R <= 8)
+  constexpr unsigned K = TILE >= 256 ? TILE / 256 : 1;   // elements per thread
+  constexpr unsigned UU = K < U ? K : U;
+  constexpr bool FULL = (TILE >= 256);                  // every thread has exactly K elements
+  const unsigned tid = threadIdx.x;
   if (ROWS) {
+    const unsigned sidx0 = (tid >> R) * PITCH_L + (tid & (NPTS - 1));
+    constexpr unsigned SSTEP = (R <= 8 ? (256u >> R) : 0u) * PITCH_L;
 #pragma unroll 1
-    for (unsigned e0 = threadIdx.x; e0 < TILE; e0 += U * 256) {
-      uint32_t x[U];
+    for (unsigned k0 = 0; k0 < K; k0 += UU) {
+      uint32_t x[UU];
 #pragma unroll
-      for (unsigned u = 0; u < U; u++) {
-        unsigned e = e0 + u * 256;
+      for (unsigned u = 0; u < UU; u++) {
+        unsigned e = tid + (k0 + u) * 256;
         size_t g = base + e;
         x[u] = 0;
-        if (e < TILE && g < a.total) x[u] = a.ebits ? __ldg(a.in + (g >> a.ebits)) : a.in[g];
+        if ((FULL || e < TILE) && g < a.total) x[u] = a.ebits ? __ldg(a.in + (g >> a.ebits)) : a.in[g];
       }
 #pragma unroll
-      for (unsigned u = 0; u < U; u++) {
-        unsigned e = e0 + u * 256;
-        if (e < TILE) sm[(e >> R) * PITCH_L + (e & (NPTS - 1))] = x[u];
+      for (unsigned u = 0; u < UU; u++) {
+        unsigned e = tid + (k0 + u) * 256;
+        if (FULL || e < TILE) sm[sidx0 + (k0 + u) * SSTEP] = x[u];
       }
     }
   } else {
     const uint32_t* src = a.in + base;
     const uint32_t tbase = (uint32_t)base & twist_mask32;
+    const uint32_t off0 = ((tid >> 5) << a.s_lo) + (tid & 31);
+    const uint32_t ostep = 8u << a.s_lo;
+    const bool tw_on = !INV && a.pass_twist;
 #pragma unroll 1
-    for (unsigned e0 = threadIdx.x; e0 < TILE; e0 += U * 256) {
-      uint32_t x[U], tw[U];
+    for (unsigned k0 = 0; k0 < K; k0 += UU) {
+      uint32_t x[UU], tw[UU];
 #pragma unroll
-      for (unsigned u = 0; u < U; u++) {
-        unsigned e = e0 + u * 256;
-        unsigned p = e >> 5, l = e & 31;
+      for (unsigned u = 0; u < UU; u++) {
+        unsigned e = tid + (k0 + u) * 256;
         x[u] = 0;
         tw[u] = 0;
-        if (e < TILE) {
-          size_t off = ((size_t)p << a.s_lo) + l;
+        if (FULL || e < TILE) {
+          uint32_t off = off0 + (k0 + u) * ostep;
           x[u] = src[off];
-          if (!INV && a.pass_twist) tw[u] = __ldg(a.pass_twist + ((tbase + (uint32_t)off) & twist_mask32));
+          if (tw_on) tw[u] = __ldg(a.pass_twist + ((tbase + off) & twist_mask32));
         }
       }
 #pragma unroll
-      for (unsigned u = 0; u < U; u++) {
-        unsigned e = e0 + u * 256;
-        if (e < TILE) sm[e] = (!INV && a.pass_twist) ? fp_mul(x[u], tw[u]) : x[u];
+      for (unsigned u = 0; u < UU; u++) {
+        unsigned e = tid + (k0 + u) * 256;
+        if (FULL || e < TILE) sm[e] = tw_on ? fp_mul(x[u], tw[u]) : x[u];
       }
     }
   }
@@ -273,25 +283,28 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(PassArgs a) {
   // ---- store (inverse: inter-pass twist / final scale applied here) ----
   if (ROWS) {
     const uint32_t nmask = (uint32_t)(((size_t)1 << a.logn) - 1);
+    const unsigned sidx0 = (tid >> R) * PITCH_L + (tid & (NPTS - 1));
+    constexpr unsigned SSTEP = (R <= 8 ? (256u >> R) : 0u) * PITCH_L;
+    const bool tab_on = a.apply_scale && a.scale_tab;
 #pragma unroll 1
-    for (unsigned e0 = threadIdx.x; e0 < TILE; e0 += U * 256) {
-      uint32_t tw[U];
+    for (unsigned k0 = 0; k0 < K; k0 += UU) {
+      uint32_t tw[UU];
 #pragma unroll
-      for (unsigned u = 0; u < U; u++) {
-        unsigned e = e0 + u * 256;
+      for (unsigned u = 0; u < UU; u++) {
+        unsigned e = tid + (k0 + u) * 256;
         size_t g = base + e;
         tw[u] = 0;
-        if (a.apply_scale && a.scale_tab && e < TILE && g < a.total) tw[u] = __ldg(a.scale_tab + ((uint32_t)g & nmask));
+        if (tab_on && (FULL || e < TILE) && g < a.total) tw[u] = __ldg(a.scale_tab + ((uint32_t)g & nmask));
       }
 #pragma unroll
-      for (unsigned u = 0; u < U; u++) {
-        unsigned e = e0 + u * 256;
+      for (unsigned u = 0; u < UU; u++) {
+        unsigned e = tid + (k0 + u) * 256;
         size_t g = base + e;
-        if (e >= TILE || g >= a.total) continue;
-        uint32_t x = sm[(e >> R) * PITCH_L + (e & (NPTS - 1))];
+        if (!(FULL || e < TILE) || g >= a.total) continue;
+        uint32_t x = sm[sidx0 + (k0 + u) * SSTEP];
         if (a.apply_scale) {
           x = fp_mul(x, a.scale);
-          if (a.scale_tab) x = fp_mul(x, tw[u]);
+          if (tab_on) x = fp_mul(x, tw[u]);
         }
         a.out[g] = x;
       }
@@ -299,24 +312,25 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(PassArgs a) {
   } else {
     uint32_t* dst = a.out + base;
     const uint32_t tbase = (uint32_t)base & twist_mask32;
+    const uint32_t off0 = ((tid >> 5) << a.s_lo) + (tid & 31);
+    const uint32_t ostep = 8u << a.s_lo;
+    const bool tw_on = INV && a.pass_twist;
 #pragma unroll 1
-    for (unsigned e0 = threadIdx.x; e0 < TILE; e0 += U * 256) {
-      uint32_t tw[U];
+    for (unsigned k0 = 0; k0 < K; k0 += UU) {
+      uint32_t tw[UU];
 #pragma unroll
-      for (unsigned u = 0; u < U; u++) {
-        unsigned e = e0 + u * 256;
-        unsigned p = e >> 5, l = e & 31;
+      for (unsigned u = 0; u < UU; u++) {
+        unsigned e = tid + (k0 + u) * 256;
         tw[u] = 0;
-        if (INV && a.pass_twist && e < TILE) tw[u] = __ldg(a.pass_twist + ((tbase + (uint32_t)(((size_t)p << a.s_lo) + l)) & twist_mask32));
+        if (tw_on && (FULL || e < TILE)) tw[u] = __ldg(a.pass_twist + ((tbase + off0 + (k0 + u) * ostep) & twist_mask32));
       }
 #pragma unroll
-      for (unsigned u = 0; u < U; u++) {
-        unsigned e = e0 + u * 256;
-        if (e >= TILE) continue;
-        unsigned p = e >> 5, l = e & 31;
+      for (unsigned u = 0; u < UU; u++) {
+        unsigned e = tid + (k0 + u) * 256;
+        if (!(FULL || e < TILE)) continue;
         uint32_t x = sm[e];
-        if (INV && a.pass_twist) x = fp_mul(x, tw[u]);
-        dst[((size_t)p << a.s_lo) + l] = x;
+        if (tw_on) x = fp_mul(x, tw[u]);
+        dst[off0 + (k0 + u) * ostep] = x;
       }
     }
   }
