@@ -6,9 +6,13 @@
 
 namespace b2z {
 b2z_err merkle_build(b2z_ctx* ctx, uint32_t* nodes, const uint32_t* matrix, size_t rows, size_t cols);
+struct WitnessReady;
 b2z_err prove_segment_device(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, const uint32_t* code_dev, const uint32_t* data_dev,
                              const uint32_t* globals_host, const uint32_t* accum_noise_dev, size_t zk_rows, uint32_t* seal_host,
-                             size_t* seal_words_out);
+                             size_t* seal_words_out, const WitnessReady* ready);
+b2z_err prove_segment_host(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, const uint32_t* code_host, const uint32_t* data_host,
+                           const uint32_t* globals_host, const uint32_t* accum_noise_host, size_t zk_rows, uint32_t* seal_host,
+                           size_t* seal_words);
 b2z_err eval_check_launch(b2z_ctx* ctx, const b2z_circuit* c, uint32_t* check, const uint32_t* const groups[3], const uint32_t* globals_dev,
                           const uint32_t* mix_dev, const Fp4& poly_mix, unsigned po2);
 b2z_err witgen_launch(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, uint32_t* code, uint32_t* data, uint32_t* globals_dev,
@@ -62,6 +66,8 @@ b2z_err b2z_destroy(b2z_ctx* ctx) {
     cudaEventDestroy(pr.first);
     cudaEventDestroy(pr.second);
   }
+  for (auto e : ctx->h2d_events) cudaEventDestroy(e);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   cudaStreamDestroy(ctx->own_stream);
   delete ctx;
   return nullptr;
@@ -246,27 +252,14 @@ b2z_err b2z_prove_segment_device(b2z_ctx* ctx, const b2z_circuit* c, unsigned po
                                  size_t* seal_words) {
   CTX_GUARD();
   B2Z_REQUIRE(c && seal_host, "null argument");
-  return prove_segment_device(ctx, c, po2, code_dev, data_dev, globals_host, accum_noise_dev, zk_rows, seal_host, seal_words);
+  return prove_segment_device(ctx, c, po2, code_dev, data_dev, globals_host, accum_noise_dev, zk_rows, seal_host, seal_words, nullptr);
 }
 b2z_err b2z_prove_segment(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, const uint32_t* code_host, const uint32_t* data_host,
                           const uint32_t* globals_host, const uint32_t* accum_noise_host, size_t zk_rows, uint32_t* seal_host,
                           size_t* seal_words) {
   CTX_GUARD();
   B2Z_REQUIRE(c && seal_host, "null argument");
-  size_t n = (size_t)1 << po2;
-  size_t wa = c->group_size[0], wc = c->group_size[1], wd = c->group_size[2];
-  uint32_t *code = nullptr, *data = nullptr, *noise = nullptr;
-  B2Z_CUDA(cudaMallocAsync(&code, 4 * wc * n, ctx->stream));
-  B2Z_CUDA(cudaMallocAsync(&data, 4 * wd * n, ctx->stream));
-  B2Z_CUDA(cudaMallocAsync(&noise, 4 * (wa * zk_rows + 1), ctx->stream));
-  B2Z_CUDA(cudaMemcpyAsync(code, code_host, 4 * wc * n, cudaMemcpyHostToDevice, ctx->stream));
-  B2Z_CUDA(cudaMemcpyAsync(data, data_host, 4 * wd * n, cudaMemcpyHostToDevice, ctx->stream));
-  B2Z_CUDA(cudaMemcpyAsync(noise, accum_noise_host, 4 * wa * zk_rows, cudaMemcpyHostToDevice, ctx->stream));
-  b2z_err err = prove_segment_device(ctx, c, po2, code, data, globals_host, noise, zk_rows, seal_host, seal_words);
-  cudaFreeAsync(code, ctx->stream);
-  cudaFreeAsync(data, ctx->stream);
-  cudaFreeAsync(noise, ctx->stream);
-  return err;
+  return prove_segment_host(ctx, c, po2, code_host, data_host, globals_host, accum_noise_host, zk_rows, seal_host, seal_words);
 }
 size_t b2z_last_phase_ms(const b2z_ctx* ctx, double* ms, size_t cap) {
   if (!ctx) return 0;

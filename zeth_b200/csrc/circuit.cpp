@@ -287,7 +287,10 @@ void circuit_codegen(b2z_circuit* c) {
     << (c->group_size[1] ? c->group_size[1] : 1) << "]; const u32* g2[" << (c->group_size[2] ? c->group_size[2] : 1) << "]; };\n";
   unsigned max_back = 0;
   for (size_t t = 0; t < c->n_taps; t++) max_back = std::max(max_back, c->tap_back[t]);
-  o << "extern \"C\" __global__ void __launch_bounds__(128, 4) b2z_eval_check(u32* __restrict__ check, const __grid_constant__ ColPtrs cp, "
+  // register cap = 65536 / (128 * min_blocks); tunable for experiments through B2Z_EVALCHECK_MINBLOCKS
+  int min_blocks = 8;
+  if (const char* e = getenv("B2Z_EVALCHECK_MINBLOCKS")) min_blocks = atoi(e) > 0 ? atoi(e) : 8;
+  o << "extern \"C\" __global__ void __launch_bounds__(128, " << min_blocks << ") b2z_eval_check(u32* __restrict__ check, const __grid_constant__ ColPtrs cp, "
        "const u32* __restrict__ globals, const u32* __restrict__ mixg, "
        "const u32* __restrict__ pm, u32 iz0, u32 iz1, u32 iz2, u32 iz3, u64 mask) {\n";
   o << "  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;\n  if (i > mask) return;\n  const u64 domain = mask + 1;\n";

@@ -41,6 +41,8 @@ struct b2z_ctx {
   int sm_count = 148;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;          // host->device witness uploads overlapped with compute (b2z_prove_segment)
+  std::vector<cudaEvent_t> h2d_events;
   uint64_t launches = 0;
   // per-size device tables, built lazily: forward / inverse twiddles w_n^k (k < n/2), 3^rev(j) for zk_shift
   uint32_t* tw_fwd[b2z::MAX_PO2 + 1] = {};

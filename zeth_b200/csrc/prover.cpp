@@ -107,7 +107,10 @@ static b2z_err ensure_pinned(b2z_ctx* ctx, size_t words) {
   return nullptr;
 }
 
+struct PolyGroupDev;
+struct Seal;
 // PolyGroup::new + merkle.commit: coeffs (bit-reversed, shifted) -> LDE, natural-order coeffs, Merkle tree, top layer + root
+static b2z_err poly_group_finish(b2z_ctx* ctx, DevMem& mem, PolyGroupDev& pg, unsigned po2, Seal& seal, HostRng& rng);
 static b2z_err poly_group_commit(b2z_ctx* ctx, DevMem& mem, PolyGroupDev& pg, uint32_t* coeffs, size_t count, unsigned po2, Seal& seal,
                                  HostRng& rng) {
   size_t n = (size_t)1 << po2, domain = 4 * n;
@@ -116,6 +119,13 @@ static b2z_err poly_group_commit(b2z_ctx* ctx, DevMem& mem, PolyGroupDev& pg, ui
   pg.n = n;
   B2Z_TRY(mem.alloc(&pg.evaluated, count * domain));
   B2Z_TRY(launch_evaluate(ctx, pg.evaluated, coeffs, count, po2 + 2, 2));
+  return poly_group_finish(ctx, mem, pg, po2, seal, rng);
+}
+// natural-order coefficients, Merkle tree over the LDE, top layer -> seal, root -> transcript
+static b2z_err poly_group_finish(b2z_ctx* ctx, DevMem& mem, PolyGroupDev& pg, unsigned po2, Seal& seal, HostRng& rng) {
+  size_t n = (size_t)1 << po2, domain = 4 * n;
+  size_t count = pg.count;
+  uint32_t* coeffs = pg.coeffs;
   B2Z_TRY(launch_bit_reverse(ctx, coeffs, count, po2));
   B2Z_TRY(mem.alloc(&pg.nodes, 2 * domain * 8));
   B2Z_TRY(merkle_build(ctx, pg.nodes, pg.evaluated, domain, count));
@@ -130,15 +140,35 @@ static b2z_err poly_group_commit(b2z_ctx* ctx, DevMem& mem, PolyGroupDev& pg, ui
   return nullptr;
 }
 
-// prover.rs make_coeffs + commit_group
+// Optional readiness of a host-uploaded witness: the upload runs on ctx->copy_stream in column chunks, the commit
+// consumes each chunk as soon as its event fires (upload of chunk k+1 overlaps the iNTT / LDE of chunk k).
+struct WitnessReady {
+  cudaEvent_t code = nullptr, noise = nullptr;
+  std::vector<cudaEvent_t> data_chunks;  // one event per `chunk_cols` data columns
+  size_t chunk_cols = 0;
+};
+
+// prover.rs make_coeffs + commit_group (PolyGroup::new inlined so that the per-chunk work can start early)
 static b2z_err commit_group(b2z_ctx* ctx, DevMem& mem, PolyGroupDev& pg, const uint32_t* witness, size_t count, unsigned po2, Seal& seal,
-                            HostRng& rng) {
-  size_t n = (size_t)1 << po2;
+                            HostRng& rng, const std::vector<cudaEvent_t>* chunk_events = nullptr, size_t chunk_cols = 0,
+                            cudaEvent_t whole_event = nullptr) {
+  size_t n = (size_t)1 << po2, domain = 4 * n;
   uint32_t* coeffs = nullptr;
   B2Z_TRY(mem.alloc(&coeffs, count * n));
-  B2Z_CUDA(cudaMemcpyAsync(coeffs, witness, 4 * count * n, cudaMemcpyDeviceToDevice, ctx->stream));
-  B2Z_TRY(launch_interpolate(ctx, coeffs, count, po2, /*fuse_zk_shift=*/true));
-  return poly_group_commit(ctx, mem, pg, coeffs, count, po2, seal, rng);
+  pg.coeffs = coeffs;
+  pg.count = count;
+  pg.n = n;
+  B2Z_TRY(mem.alloc(&pg.evaluated, count * domain));
+  if (whole_event) B2Z_CUDA(cudaStreamWaitEvent(ctx->stream, whole_event, 0));
+  if (!chunk_events || chunk_cols == 0) chunk_cols = count;
+  for (size_t c0 = 0, k = 0; c0 < count; c0 += chunk_cols, k++) {
+    size_t cols = count - c0 < chunk_cols ? count - c0 : chunk_cols;
+    if (chunk_events && k < chunk_events->size()) B2Z_CUDA(cudaStreamWaitEvent(ctx->stream, (*chunk_events)[k], 0));
+    B2Z_CUDA(cudaMemcpyAsync(coeffs + c0 * n, witness + c0 * n, 4 * cols * n, cudaMemcpyDeviceToDevice, ctx->stream));
+    B2Z_TRY(launch_interpolate(ctx, coeffs + c0 * n, cols, po2, /*fuse_zk_shift=*/true));
+    B2Z_TRY(launch_evaluate(ctx, pg.evaluated + c0 * domain, coeffs + c0 * n, cols, po2 + 2, 2));
+  }
+  return poly_group_finish(ctx, mem, pg, po2, seal, rng);
 }
 
 // unique interpolant through (x_i, fx_i) -> monomial coefficients (core/poly.rs poly_interpolate)
@@ -171,7 +201,7 @@ b2z_err mix_pow_table(b2z_ctx* ctx, uint32_t* tab, const Fp4& start, const Fp4& 
 
 b2z_err prove_segment_device(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, const uint32_t* code_dev, const uint32_t* data_dev,
                              const uint32_t* globals_host, const uint32_t* accum_noise_dev, size_t zk_rows, uint32_t* seal_host,
-                             size_t* seal_words_out) {
+                             size_t* seal_words_out, const WitnessReady* ready) {
   B2Z_REQUIRE(po2 >= 1 && po2 <= 24, "po2 out of range");
   B2Z_REQUIRE(c->library != nullptr, "circuit kernels not loaded");
   const size_t n = (size_t)1 << po2, domain = 4 * n;
@@ -205,10 +235,11 @@ b2z_err prove_segment_device(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, c
 
   PolyGroupDev pg[3], check_pg;
   tm.begin(0);
-  B2Z_TRY(commit_group(ctx, mem, pg[B2Z_GROUP_CODE], code_dev, wc, po2, seal, rng));
+  B2Z_TRY(commit_group(ctx, mem, pg[B2Z_GROUP_CODE], code_dev, wc, po2, seal, rng, nullptr, 0, ready ? ready->code : nullptr));
   tm.end(0);
   tm.begin(1);
-  B2Z_TRY(commit_group(ctx, mem, pg[B2Z_GROUP_DATA], data_dev, wd, po2, seal, rng));
+  B2Z_TRY(commit_group(ctx, mem, pg[B2Z_GROUP_DATA], data_dev, wd, po2, seal, rng, ready ? &ready->data_chunks : nullptr,
+                       ready ? ready->chunk_cols : 0));
   tm.end(1);
 
   std::vector<uint32_t> mix_host(msz + 1);
@@ -219,6 +250,7 @@ b2z_err prove_segment_device(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, c
   tm.begin(2);
   uint32_t* accum = nullptr;
   B2Z_TRY(mem.alloc(&accum, wa * n));
+  if (ready && ready->noise) B2Z_CUDA(cudaStreamWaitEvent(ctx->stream, ready->noise, 0));
   B2Z_TRY(launch_accum(ctx, accum, data_dev, c->accum_col_dev, c->accum_col.size(), mix_dev, accum_noise_dev, po2, zk_rows));
   tm.end(2);
   tm.begin(3);
@@ -441,6 +473,52 @@ b2z_err prove_segment_device(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, c
   memcpy(seal_host, seal.w, 4 * seal_words);
   if (seal_words_out) *seal_words_out = seal_words;
   return nullptr;
+}
+
+
+// Host buffers in, seal out.  The witness is uploaded on the copy stream in column chunks while the compute stream is
+// already committing the code group and the first data chunks (pinned host memory makes the copies truly asynchronous).
+b2z_err prove_segment_host(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, const uint32_t* code_host, const uint32_t* data_host,
+                           const uint32_t* globals_host, const uint32_t* accum_noise_host, size_t zk_rows, uint32_t* seal_host,
+                           size_t* seal_words) {
+  B2Z_REQUIRE(po2 >= 1 && po2 <= 24, "po2 out of range");
+  const size_t n = (size_t)1 << po2;
+  const size_t wa = c->group_size[0], wc = c->group_size[1], wd = c->group_size[2];
+  if (!ctx->copy_stream) B2Z_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  WitnessReady ready;
+  ready.chunk_cols = 32;
+  size_t nchunks = (wd + ready.chunk_cols - 1) / ready.chunk_cols;
+  while (ctx->h2d_events.size() < nchunks + 3) {
+    cudaEvent_t e;
+    B2Z_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->h2d_events.push_back(e);
+  }
+  uint32_t *code = nullptr, *data = nullptr, *noise = nullptr;
+  B2Z_CUDA(cudaMallocAsync(&code, 4 * (wc * n + 1), ctx->stream));
+  B2Z_CUDA(cudaMallocAsync(&data, 4 * (wd * n + 1), ctx->stream));
+  B2Z_CUDA(cudaMallocAsync(&noise, 4 * (wa * zk_rows + 1), ctx->stream));
+  // the copy stream may only touch the buffers once the (stream-ordered) allocations are visible
+  cudaEvent_t alloc_done = ctx->h2d_events[nchunks + 2];
+  B2Z_CUDA(cudaEventRecord(alloc_done, ctx->stream));
+  B2Z_CUDA(cudaStreamWaitEvent(ctx->copy_stream, alloc_done, 0));
+  B2Z_CUDA(cudaMemcpyAsync(code, code_host, 4 * wc * n, cudaMemcpyHostToDevice, ctx->copy_stream));
+  ready.code = ctx->h2d_events[nchunks];
+  B2Z_CUDA(cudaEventRecord(ready.code, ctx->copy_stream));
+  for (size_t k = 0; k < nchunks; k++) {
+    size_t c0 = k * ready.chunk_cols, cols = wd - c0 < ready.chunk_cols ? wd - c0 : ready.chunk_cols;
+    B2Z_CUDA(cudaMemcpyAsync(data + c0 * n, data_host + c0 * n, 4 * cols * n, cudaMemcpyHostToDevice, ctx->copy_stream));
+    B2Z_CUDA(cudaEventRecord(ctx->h2d_events[k], ctx->copy_stream));
+    ready.data_chunks.push_back(ctx->h2d_events[k]);
+  }
+  B2Z_CUDA(cudaMemcpyAsync(noise, accum_noise_host, 4 * wa * zk_rows, cudaMemcpyHostToDevice, ctx->copy_stream));
+  ready.noise = ctx->h2d_events[nchunks + 1];
+  B2Z_CUDA(cudaEventRecord(ready.noise, ctx->copy_stream));
+  b2z_err err = prove_segment_device(ctx, c, po2, code, data, globals_host, noise, zk_rows, seal_host, seal_words, &ready);
+  cudaStreamSynchronize(ctx->copy_stream);
+  cudaFreeAsync(code, ctx->stream);
+  cudaFreeAsync(data, ctx->stream);
+  cudaFreeAsync(noise, ctx->stream);
+  return err;
 }
 
 }  // namespace b2z
