@@ -40,7 +40,7 @@ b2z_err launch_fri_fold(b2z_ctx* ctx, uint32_t* out, const uint32_t* in, const F
 // column, 4 modular multiplies per coefficient.  A block handles EA_GROUP evaluations of the same x over one chunk of
 // coefficients so that every loaded power is reused EA_GROUP times from registers.
 constexpr unsigned EA_THREADS = 256;
-constexpr unsigned EA_PER_THREAD = 8;
+constexpr unsigned EA_PER_THREAD = 32;
 constexpr unsigned EA_GROUP = 8;
 constexpr unsigned EA_POW_RUN = 64;
 __global__ void ea_powers_kernel(uint32_t* __restrict__ pw, Fp4 x, size_t n) {
