@@ -13,8 +13,8 @@ b2z_err prove_segment_device(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, c
 b2z_err prove_segment_host(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, const uint32_t* code_host, const uint32_t* data_host,
                            const uint32_t* globals_host, const uint32_t* accum_noise_host, size_t zk_rows, uint32_t* seal_host,
                            size_t* seal_words);
-b2z_err eval_check_launch(b2z_ctx* ctx, const b2z_circuit* c, uint32_t* check, const uint32_t* const groups[3], const uint32_t* globals_dev,
-                          const uint32_t* mix_dev, const Fp4& poly_mix, unsigned po2);
+b2z_err eval_check_launch(b2z_ctx* ctx, const b2z_circuit* c, uint32_t* check, const uint32_t* const groups[3], const uint32_t* globals_host,
+                          const uint32_t* mix_host, const Fp4& poly_mix, unsigned po2);
 b2z_err witgen_launch(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, uint32_t* code, uint32_t* data, uint32_t* globals_dev,
                       uint32_t* accum_noise_dev, uint64_t seed, size_t zk_rows);
 const char* phase_name(size_t i);
@@ -231,7 +231,12 @@ b2z_err b2z_eval_check(b2z_ctx* ctx, const b2z_circuit* c, uint32_t* check, cons
                        const uint32_t* globals_dev, const uint32_t* mix_dev, const uint32_t* poly_mix_host, unsigned po2) {
   CTX_GUARD();
   B2Z_REQUIRE(c, "null circuit");
-  return eval_check_launch(ctx, c, check, groups_dev, globals_dev, mix_dev, ext_from(poly_mix_host), po2);
+  // globals / mix arrive as device arrays (Hal buffers); the kernel takes them by value, so fetch the few words
+  std::vector<uint32_t> g(c->globals_size + 1), m(c->mix_size + 1);
+  if (c->globals_size) B2Z_CUDA(cudaMemcpyAsync(g.data(), globals_dev, 4 * c->globals_size, cudaMemcpyDeviceToHost, ctx->stream));
+  if (c->mix_size) B2Z_CUDA(cudaMemcpyAsync(m.data(), mix_dev, 4 * c->mix_size, cudaMemcpyDeviceToHost, ctx->stream));
+  B2Z_CUDA(cudaStreamSynchronize(ctx->stream));
+  return eval_check_launch(ctx, c, check, groups_dev, g.data(), m.data(), ext_from(poly_mix_host), po2);
 }
 b2z_err b2z_accumulate(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, uint32_t* accum, const uint32_t* code, const uint32_t* data,
                        const uint32_t* mix_dev, const uint32_t* accum_noise_dev, size_t zk_rows) {

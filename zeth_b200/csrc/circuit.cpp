@@ -256,7 +256,8 @@ struct Emitter {
       } break;
       case OP_GET_GLOBAL:
         is_ext.push_back(0);
-        expr.push_back(std::string("ldv(") + (s.a == 0 ? "globals" : "mixg") + " + " + std::to_string(s.b) + ")");
+        if (trace_domain) expr.push_back(std::string("ldv(globals + ") + std::to_string(s.b) + ")");
+        else expr.push_back(std::string(s.a == 0 ? "kc.g[" : "kc.m[") + std::to_string(s.b) + "]");
         break;
       case OP_ADD: case OP_SUB: case OP_MUL: {
         bool ea = is_ext[s.a], eb = is_ext[s.b];
@@ -275,6 +276,11 @@ struct Emitter {
   }
 };
 
+static std::string pw_expr(uint32_t e) {
+  std::string b = std::to_string(4 * e);
+  return "emake(kc.pw[" + b + "], kc.pw[" + b + " + 1], kc.pw[" + b + " + 2], kc.pw[" + b + " + 3])";
+}
+
 void circuit_codegen(b2z_circuit* c) {
   std::ostringstream o;
   o << PRELUDE;
@@ -290,14 +296,19 @@ void circuit_codegen(b2z_circuit* c) {
   // register cap = 65536 / (128 * min_blocks); tunable for experiments through B2Z_EVALCHECK_MINBLOCKS
   int min_blocks = 8;
   if (const char* e = getenv("B2Z_EVALCHECK_MINBLOCKS")) min_blocks = atoi(e) > 0 ? atoi(e) : 8;
+  // globals, mix values and the powers of poly_mix are launch constants: they travel by value (constant bank), so
+  // they are instruction operands and cost neither loads nor registers
+  o << "struct Consts { u32 g[" << (c->globals_size ? c->globals_size : 1) << "]; u32 m[" << (c->mix_size ? c->mix_size : 1)
+    << "]; u32 pw[" << 4 * (c->max_exp + 1) << "]; };\n";
   o << "extern \"C\" __global__ void __launch_bounds__(128, " << min_blocks << ") b2z_eval_check(u32* __restrict__ check, const __grid_constant__ ColPtrs cp, "
-       "const u32* __restrict__ globals, const u32* __restrict__ mixg, "
-       "const u32* __restrict__ pm, u32 iz0, u32 iz1, u32 iz2, u32 iz3, u64 mask) {\n";
+       "const __grid_constant__ Consts kc, u32 iz0, u32 iz1, u32 iz2, u32 iz3, u64 mask) {\n";
   o << "  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;\n  if (i > mask) return;\n  const u64 domain = mask + 1;\n";
-  for (unsigned b = 0; b <= max_back; b++) o << "  const u32 ib" << b << " = (u32)((i - " << 4 * b << "ull) & mask) << 2;\n";
+  for (unsigned b = 0; b <= max_back; b++) o << "  u32 ib" << b << " = (u32)((i - " << 4 * b << "ull) & mask) << 2;\n";
   {
     Emitter em{c, false, {}, {}};
     size_t nmx = 0;
+    unsigned eqz_count = 0, fence_every = 1u << 30;
+    if (const char* e = getenv("B2Z_EVALCHECK_FENCE")) fence_every = atoi(e) > 0 ? atoi(e) : 1u << 30;
     for (const auto& s : c->steps) {
       switch (s.op) {
         case OP_TRUE:
@@ -305,13 +316,21 @@ void circuit_codegen(b2z_circuit* c) {
           nmx++;
           break;
         case OP_AND_EQZ: {
-          std::string pw = "eld(pm + " + std::to_string(4 * c->mix_exp[s.a]) + ")";
+          std::string pw = pw_expr(c->mix_exp[s.a]);
           std::string term = em.is_ext[s.b] ? "emul(" + pw + ", " + em.operand(s.b) + ")" : "emulf(" + pw + ", " + em.operand(s.b) + ")";
           o << "  const E m" << nmx << " = eadd(m" << s.a << ", " << term << ");\n";
+          // Throttle: make the row offsets of the NEXT constraint's tap loads data-dependent on this constraint's
+          // accumulator (the compare is never true: field words are < P).  Without it the scheduler issues all ~400 tap
+          // loads of the straight-line program up front and spills their results.
+          if (++eqz_count % fence_every == 0) {
+            o << "  { const u32 dep = (m" << nmx << ".a == 0xffffffffu);";
+            for (unsigned b = 0; b <= max_back; b++) o << " ib" << b << " += dep;";
+            o << " }\n";
+          }
           nmx++;
         } break;
         case OP_AND_COND: {
-          std::string pw = "eld(pm + " + std::to_string(4 * c->mix_exp[s.a]) + ")";
+          std::string pw = pw_expr(c->mix_exp[s.a]);
           std::string inner = em.is_ext[s.b] ? "emul(m" + std::to_string(s.c) + ", " + em.operand(s.b) + ")"
                                              : "emulf(m" + std::to_string(s.c) + ", " + em.operand(s.b) + ")";
           o << "  const E m" << nmx << " = eadd(m" << s.a << ", emul(" << inner << ", " << pw << "));\n";

@@ -195,8 +195,8 @@ static void hash_info(const uint8_t* info, uint32_t* dg) {
   host_hash_elem_slice(e, 16, dg);
 }
 
-b2z_err eval_check_launch(b2z_ctx* ctx, const b2z_circuit* c, uint32_t* check, const uint32_t* const groups[3], const uint32_t* globals_dev,
-                          const uint32_t* mix_dev, const Fp4& poly_mix, unsigned po2);
+b2z_err eval_check_launch(b2z_ctx* ctx, const b2z_circuit* c, uint32_t* check, const uint32_t* const groups[3], const uint32_t* globals_host,
+                          const uint32_t* mix_host, const Fp4& poly_mix, unsigned po2);
 b2z_err mix_pow_table(b2z_ctx* ctx, uint32_t* tab, const Fp4& start, const Fp4& mix, size_t n);
 
 b2z_err prove_segment_device(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, const uint32_t* code_dev, const uint32_t* data_dev,
@@ -268,7 +268,7 @@ b2z_err prove_segment_device(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, c
   tm.begin(4);
   {
     const uint32_t* groups[3] = {pg[0].evaluated, pg[1].evaluated, pg[2].evaluated};
-    B2Z_TRY(eval_check_launch(ctx, c, check, groups, globals_dev, mix_dev, poly_mix, po2));
+    B2Z_TRY(eval_check_launch(ctx, c, check, groups, globals_host, mix_host.data(), poly_mix, po2));
   }
   tm.end(4);
   tm.begin(5);
