@@ -124,6 +124,10 @@ b2z_err b2z_prove_segment_device(b2z_ctx* ctx, const b2z_circuit* c, unsigned po
 b2z_err b2z_prove_segment(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, const uint32_t* code_host, const uint32_t* data_host,
                           const uint32_t* globals_host, const uint32_t* accum_noise_host, size_t zk_rows, uint32_t* seal_host,
                           size_t* seal_words);
+/* Per-segment STARK verifier on the host CPU: what `receipt.verify(image_id)` (/root/reference crates/host/src/bin/cli.rs:103)
+ * runs for each SegmentReceipt seal (risc0-zkp verify/mod.rs).  Needs no GPU (load the circuit with ctx == NULL).
+ * Returns 0 if the seal is accepted, a positive rejection code otherwise, -1 on bad arguments. */
+int b2z_verify_segment(const b2z_circuit* c, const uint32_t* seal, size_t seal_words);
 /* per-phase device milliseconds of the last prove call on this context (names via b2z_phase_name; returns count) */
 size_t b2z_last_phase_ms(const b2z_ctx* ctx, double* ms, size_t cap);
 const char* b2z_phase_name(size_t i);

@@ -82,3 +82,23 @@ def test_no_cpu_fallback():
     L = H.load_library()
     err = L.b2z_hash_rows(None, None, None, C.c_size_t(4), C.c_size_t(4))
     assert err and b"null context" in err
+
+
+def test_product_verifier_matches_oracle_verifier(oracle):
+    """b2z_verify_segment (product, host CPU) against the oracle's verifier: same accept / reject decisions and codes."""
+    for mk, po2 in ((S.circuit_tiny, 6), (S.circuit_tiny, 10), (S.circuit_small, 12)):
+        sc = mk()
+        oc = oracle.Circuit(sc.blob)
+        c = H.Circuit(None, sc.blob)
+        n = 1 << po2
+        zk = min(1994, n // 4)
+        code, data, glob, noise = oc.witgen(po2, 31 + po2, zk)
+        seal = oc.prove(po2, code, data, glob, noise, zk)
+        assert c.verify(seal) == 0 and oc.verify(seal) == 0
+        rng = np.random.default_rng(po2)
+        for pos in list(rng.integers(0, seal.size, size=25)) + [0, sc.globals_size, seal.size - 1]:
+            bad = seal.copy()
+            bad[pos] ^= 1 << int(rng.integers(0, 31))
+            assert c.verify(bad) == oc.verify(bad) != 0
+        assert c.verify(seal[:-3]) == oc.verify(seal[:-3]) != 0
+        c.close()

@@ -35,6 +35,25 @@ def test_batch_expand_into_evaluate_ntt(hal, oracle, po2, count):
     assert np.array_equal(got, oracle.batch_expand_into_evaluate_ntt(x, count, 2))
 
 
+@pytest.mark.parametrize("in_po2", [22, 24])
+def test_expand_ntt_maximum_sizes(hal, oracle, in_po2):
+    """LDE domains 2^24 (po2 = 22 segment) and 2^26 (po2 = 24, the largest the protocol allows): 3- and 4-pass plans."""
+    rng = np.random.default_rng(250 + in_po2)
+    x = rand_fp(rng, 1 << in_po2)
+    d = hal.copy_from(x)
+    o = hal.alloc(1 << (in_po2 + 2))
+    hal.batch_expand_into_evaluate_ntt(o, d, 1, in_po2, 2)
+    got = hal.view(o, 1 << (in_po2 + 2))
+    want = oracle.batch_expand_into_evaluate_ntt(x, 1, 2)
+    assert np.array_equal(got, want)
+    # and back: interpolate the LDE, the first quarter (bit-reversed) holds the original coefficients
+    hal.batch_interpolate_ntt(o, 1, in_po2 + 2)
+    back = hal.view(o, 1 << (in_po2 + 2))
+    hal.free(d)
+    hal.free(o)
+    assert np.array_equal(back, oracle.batch_interpolate_ntt(want, 1))
+
+
 @pytest.mark.parametrize("po2,count", [(3, 2), (10, 3), (15, 2), (17, 1)])
 def test_batch_evaluate_ntt_roundtrip(hal, oracle, po2, count):
     rng = np.random.default_rng(300 + po2)

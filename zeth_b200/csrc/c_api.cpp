@@ -19,6 +19,7 @@ b2z_err witgen_launch(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, uint32_t
                       uint32_t* accum_noise_dev, uint64_t seed, size_t zk_rows);
 const char* phase_name(size_t i);
 void ntt_release_tables(b2z_ctx* ctx);
+int verify_segment(const b2z_circuit* c, const uint32_t* seal, size_t seal_words);
 }  // namespace b2z
 using namespace b2z;
 
@@ -274,6 +275,10 @@ size_t b2z_last_phase_ms(const b2z_ctx* ctx, double* ms, size_t cap) {
 }
 const char* b2z_phase_name(size_t i) { return phase_name(i); }
 
+int b2z_verify_segment(const b2z_circuit* c, const uint32_t* seal, size_t seal_words) {
+  if (!c || !seal) return -1;
+  return verify_segment(c, seal, seal_words);
+}
 void b2z_host_poseidon2_mix(uint32_t* s) { host_poseidon2_mix(s); }
 void b2z_host_hash_elem_slice(const uint32_t* e, size_t n, uint32_t* d) { host_hash_elem_slice(e, n, d); }
 

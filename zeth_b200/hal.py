@@ -99,6 +99,13 @@ class Circuit:
             load_library().b2z_circuit_free(self.h)
             self.h = C.c_void_p()
 
+    def verify(self, seal) -> int:
+        """Host-side STARK verifier (receipt.verify for one segment): 0 = accepted, else a rejection code."""
+        s = _u32(seal)
+        L = load_library()
+        L.b2z_verify_segment.restype = C.c_int
+        return int(L.b2z_verify_segment(self.h, _vp(s), C.c_size_t(s.size)))
+
     @staticmethod
     def precompile(blob):
         blob = _u32(blob)
