@@ -28,9 +28,10 @@ def test_seal_parity_host_api(hal, oracle, mk, po2):
     diff = np.nonzero(got != want)[0]
     assert diff.size == 0, f"first differing seal word {diff[:5]} of {want.size}"
     assert oc.verify(got) == 0
+    assert c.verify(got) == 0  # product-side host verifier (receipt.verify)
     bad = got.copy()
     bad[bad.size // 3] ^= 1
-    assert oc.verify(bad) != 0
+    assert oc.verify(bad) != 0 and c.verify(bad) != 0
     c.close()
 
 
@@ -78,4 +79,42 @@ def test_seal_parity_device_api_planning_circuit(hal, oracle):
     got = hal.prove_segment_device(c, po2, dcode, ddata, glob, dnoise, zk)
     assert np.array_equal(got, want)
     assert oc.verify(got) == 0
+    c.close()
+
+
+def test_golden_seal_digests_on_gpu(hal, oracle):
+    """The committed regression digests (tests/golden/oracle_seals.json) must be reproduced by the CUDA pipeline."""
+    import hashlib
+    import json
+    import os
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_seals.json")))
+    mk = {"tiny": S.circuit_tiny, "small": S.circuit_small}
+    for case in gold["cases"]:
+        sc = mk[case["circuit"]]()
+        oc, code, data, glob, noise, zk = _witness(oracle, sc, case["po2"], case["seed"])
+        c = H.Circuit(hal, sc.blob)
+        seal = hal.prove_segment(c, case["po2"], code, data, glob, noise, zk)
+        assert seal.size == case["seal_words"]
+        assert hashlib.sha256(seal.tobytes()).hexdigest() == case["sha256"]
+        c.close()
+
+
+def test_full_gpu_pipeline_witgen_to_seal(hal, oracle):
+    """Witness produced on the GPU (witgen kernels), proved on the GPU, checked by both verifiers; the oracle given the
+    same seed must produce the same seal (end-to-end property at a size where the oracle still finishes quickly)."""
+    sc = S.circuit_planning()
+    po2, seed = 13, 0xB2000000 + 1000
+    n = 1 << po2
+    zk = min(1994, n // 4)
+    wa, wc, wd = sc.group_sizes
+    c = H.Circuit(hal, sc.blob)
+    dcode, ddata = hal.alloc(wc * n), hal.alloc(wd * n)
+    dglob, dnoise = hal.alloc(sc.globals_size), hal.alloc(wa * zk)
+    hal.witgen(c, po2, dcode, ddata, dglob, dnoise, seed, zk)
+    glob = hal.view(dglob, sc.globals_size)
+    seal = hal.prove_segment_device(c, po2, dcode, ddata, glob, dnoise, zk)
+    assert c.verify(seal) == 0
+    oc, code, data, oglob, noise, _ = _witness(oracle, sc, po2, seed)
+    assert np.array_equal(glob, oglob)
+    assert np.array_equal(seal, oc.prove(po2, code, data, oglob, noise, zk))
     c.close()
