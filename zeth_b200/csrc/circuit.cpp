@@ -224,61 +224,152 @@ __device__ __forceinline__ E eld(const u32* p) {
 }
 )CUDA";
 
-// Straight-line emission.  Leaf steps (Const, ConstExt, Get, GetGlobal) are never materialised as variables: they are
-// re-emitted as expressions at every use, so a tap value lives only for the instruction that consumes it.  Interior
-// steps (Add/Sub/Mul) become one `const` variable each, in program order.
+// Straight-line emission with component-wise constant propagation.
+//   * every value is 1 (base field) or 4 (extension) scalar operands; an operand is a compile-time constant (Montgomery
+//     form) or the name of a `const u32` temporary / constant-bank parameter;
+//   * products and sums fold constants: x*0 = 0, x*1 = x, x+0 = x.  Programs in this vocabulary build extension values
+//     as sum_k e_k * x_k (ConstExt basis vectors) -- folding turns those 16-product ext multiplications into moves;
+//   * leaf steps (Get) are re-materialised as a fresh load at every use, so a tap value lives for one instruction.
+struct Opd {
+  bool is_const = true;
+  uint32_t k = 0;     // Montgomery constant when is_const
+  std::string name;   // expression otherwise
+  std::string str() const { return is_const ? std::to_string(k) + "u" : name; }
+};
+struct Val {
+  bool ext = false;
+  Opd c[4];
+  bool leaf_load = false;  // re-emit the load at each use
+  std::string load_expr;
+};
 struct Emitter {
   const b2z_circuit* c;
   bool trace_domain;  // witgen: taps address the trace (stride 1) instead of the 4x LDE (stride 4)
-  std::vector<std::string> expr;
-  std::vector<uint8_t> is_ext;
-  unsigned max_back = 0;
-  std::string operand(size_t v) const { return expr[v]; }
-  void step(std::ostringstream& o, const b2z_circuit::Step& s) {
-    size_t nf = expr.size();
+  std::ostringstream* o;
+  std::vector<Val> vals;
+  unsigned tmp = 0;
+  static Opd konst(uint32_t k) { Opd r; r.is_const = true; r.k = k; return r; }
+  static Opd named(const std::string& n) { Opd r; r.is_const = false; r.name = n; return r; }
+  Opd emit(const std::string& expr) {
+    std::string n = "t" + std::to_string(tmp++);
+    *o << "  const u32 " << n << " = " << expr << ";\n";
+    return named(n);
+  }
+  Opd s_mul(const Opd& a, const Opd& b) {
+    if (a.is_const && b.is_const) return konst(fp_mul(a.k, b.k));
+    if (a.is_const) {
+      if (a.k == 0) return konst(0);
+      if (a.k == MONT_ONE) return b;
+    }
+    if (b.is_const) {
+      if (b.k == 0) return konst(0);
+      if (b.k == MONT_ONE) return a;
+    }
+    return emit("fmul(" + a.str() + ", " + b.str() + ")");
+  }
+  Opd s_add(const Opd& a, const Opd& b) {
+    if (a.is_const && b.is_const) return konst(fp_add(a.k, b.k));
+    if (a.is_const && a.k == 0) return b;
+    if (b.is_const && b.k == 0) return a;
+    return emit("fadd(" + a.str() + ", " + b.str() + ")");
+  }
+  Opd s_sub(const Opd& a, const Opd& b) {
+    if (a.is_const && b.is_const) return konst(fp_sub(a.k, b.k));
+    if (b.is_const && b.k == 0) return a;
+    return emit("fsub(" + a.str() + ", " + b.str() + ")");
+  }
+  // operand view of a value; leaves are loaded here (fresh temporary per use)
+  Val use(size_t v) {
+    Val r = vals[v];
+    if (r.leaf_load) {
+      r.c[0] = emit(r.load_expr);
+      r.leaf_load = false;
+    }
+    return r;
+  }
+  static Val base(const Opd& x) {
+    Val r;
+    r.ext = false;
+    r.c[0] = x;
+    return r;
+  }
+  Val v_add(const Val& x, const Val& y, bool sub) {
+    Val r;
+    r.ext = x.ext | y.ext;
+    int n = r.ext ? 4 : 1;
+    for (int i = 0; i < n; i++) {
+      Opd a = (i == 0 || x.ext) ? x.c[i] : konst(0);
+      Opd b = (i == 0 || y.ext) ? y.c[i] : konst(0);
+      r.c[i] = sub ? s_sub(a, b) : s_add(a, b);
+    }
+    return r;
+  }
+  Val v_mul(const Val& x, const Val& y) {
+    Val r;
+    r.ext = x.ext | y.ext;
+    if (!x.ext && !y.ext) {
+      r.c[0] = s_mul(x.c[0], y.c[0]);
+    } else if (x.ext != y.ext) {
+      const Val& e = x.ext ? x : y;
+      const Opd& b = x.ext ? y.c[0] : x.c[0];
+      for (int i = 0; i < 4; i++) r.c[i] = s_mul(e.c[i], b);
+    } else {
+      const Opd beta = konst(MONT_BETA);
+      const Opd *a = x.c, *b = y.c;
+      r.c[0] = s_add(s_mul(a[0], b[0]), s_mul(beta, s_add(s_add(s_mul(a[1], b[3]), s_mul(a[2], b[2])), s_mul(a[3], b[1]))));
+      r.c[1] = s_add(s_add(s_mul(a[0], b[1]), s_mul(a[1], b[0])), s_mul(beta, s_add(s_mul(a[2], b[3]), s_mul(a[3], b[2]))));
+      r.c[2] = s_add(s_add(s_add(s_mul(a[0], b[2]), s_mul(a[1], b[1])), s_mul(a[2], b[0])), s_mul(beta, s_mul(a[3], b[3])));
+      r.c[3] = s_add(s_add(s_mul(a[0], b[3]), s_mul(a[1], b[2])), s_add(s_mul(a[2], b[1]), s_mul(a[3], b[0])));
+    }
+    return r;
+  }
+  void step(const b2z_circuit::Step& s) {
+    Val r;
     switch (s.op) {
       case OP_CONST:
-        is_ext.push_back(0);
-        expr.push_back(std::to_string(fp_from_u32(s.a)) + "u");
+        r = base(konst(fp_from_u32(s.a)));
         break;
       case OP_CONST_EXT:
-        is_ext.push_back(1);
-        expr.push_back("emake(" + std::to_string(fp_from_u32(s.a)) + "u, " + std::to_string(fp_from_u32(s.b)) + "u, " +
-                       std::to_string(fp_from_u32(s.c)) + "u, " + std::to_string(fp_from_u32(s.d)) + "u)");
+        r.ext = true;
+        r.c[0] = konst(fp_from_u32(s.a));
+        r.c[1] = konst(fp_from_u32(s.b));
+        r.c[2] = konst(fp_from_u32(s.c));
+        r.c[3] = konst(fp_from_u32(s.d));
         break;
       case OP_GET: {
-        is_ext.push_back(0);
         uint32_t g = c->tap_group[s.a], col = c->tap_offset[s.a], back = c->tap_back[s.a];
-        unsigned stride = trace_domain ? 1 : 4;
-        (void)stride;
-        expr.push_back("ldc(cp.g" + std::to_string(g) + "[" + std::to_string(col) + "], ib" + std::to_string(back) + ")");
-        if (back > max_back) max_back = back;
+        r.ext = false;
+        r.leaf_load = true;
+        r.load_expr = "ldc(cp.g" + std::to_string(g) + "[" + std::to_string(col) + "], ib" + std::to_string(back) + ")";
       } break;
       case OP_GET_GLOBAL:
-        is_ext.push_back(0);
-        if (trace_domain) expr.push_back(std::string("ldv(globals + ") + std::to_string(s.b) + ")");
-        else expr.push_back(std::string(s.a == 0 ? "kc.g[" : "kc.m[") + std::to_string(s.b) + "]");
+        if (trace_domain) {
+          r.ext = false;
+          r.leaf_load = true;
+          r.load_expr = "ldv(globals + " + std::to_string(s.b) + ")";
+        } else {
+          r = base(named(std::string(s.a == 0 ? "kc.g[" : "kc.m[") + std::to_string(s.b) + "]"));
+        }
         break;
-      case OP_ADD: case OP_SUB: case OP_MUL: {
-        bool ea = is_ext[s.a], eb = is_ext[s.b];
-        std::string A = operand(s.a), Bn = operand(s.b), e;
-        if (!ea && !eb) e = std::string(s.op == OP_ADD ? "fadd" : s.op == OP_SUB ? "fsub" : "fmul") + "(" + A + ", " + Bn + ")";
-        else if (ea && eb) e = std::string(s.op == OP_ADD ? "eadd" : s.op == OP_SUB ? "esub" : "emul") + "(" + A + ", " + Bn + ")";
-        else if (ea && !eb) e = std::string(s.op == OP_ADD ? "eaddf" : s.op == OP_SUB ? "esubf" : "emulf") + "(" + A + ", " + Bn + ")";
-        else e = s.op == OP_ADD ? "eaddf(" + Bn + ", " + A + ")" : s.op == OP_SUB ? "fsube(" + A + ", " + Bn + ")" : "emulf(" + Bn + ", " + A + ")";
-        is_ext.push_back(ea | eb);
-        std::string name = std::string((ea | eb) ? "e" : "f") + std::to_string(nf);
-        o << "  const " << ((ea | eb) ? "E " : "u32 ") << name << " = " << e << ";\n";
-        expr.push_back(name);
-      } break;
+      case OP_ADD: r = v_add(use(s.a), use(s.b), false); break;
+      case OP_SUB: r = v_add(use(s.a), use(s.b), true); break;
+      case OP_MUL: r = v_mul(use(s.a), use(s.b)); break;
       default: break;
     }
+    vals.push_back(r);
   }
 };
 
-static std::string pw_expr(uint32_t e) {
-  std::string b = std::to_string(4 * e);
-  return "emake(kc.pw[" + b + "], kc.pw[" + b + " + 1], kc.pw[" + b + " + 2], kc.pw[" + b + " + 3])";
+static Val pw_val(uint32_t e) {
+  Val r;
+  r.ext = true;
+  if (e == 0) {
+    r.c[0] = Emitter::konst(MONT_ONE);
+    for (int i = 1; i < 4; i++) r.c[i] = Emitter::konst(0);
+  } else {
+    for (int i = 0; i < 4; i++) r.c[i] = Emitter::named("kc.pw[" + std::to_string(4 * e + i) + "]");
+  }
+  return r;
 }
 
 void circuit_codegen(b2z_circuit* c) {
@@ -303,56 +394,46 @@ void circuit_codegen(b2z_circuit* c) {
   o << "extern \"C\" __global__ void __launch_bounds__(128, " << min_blocks << ") b2z_eval_check(u32* __restrict__ check, const __grid_constant__ ColPtrs cp, "
        "const __grid_constant__ Consts kc, u32 iz0, u32 iz1, u32 iz2, u32 iz3, u64 mask) {\n";
   o << "  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;\n  if (i > mask) return;\n  const u64 domain = mask + 1;\n";
-  for (unsigned b = 0; b <= max_back; b++) o << "  u32 ib" << b << " = (u32)((i - " << 4 * b << "ull) & mask) << 2;\n";
+  for (unsigned b = 0; b <= max_back; b++) o << "  const u32 ib" << b << " = (u32)((i - " << 4 * b << "ull) & mask) << 2;\n";
   {
-    Emitter em{c, false, {}, {}};
-    size_t nmx = 0;
-    unsigned eqz_count = 0, fence_every = 1u << 30;
-    if (const char* e = getenv("B2Z_EVALCHECK_FENCE")) fence_every = atoi(e) > 0 ? atoi(e) : 1u << 30;
+    Emitter em{c, false, &o, {}, 0};
+    std::vector<Val> mixv;  // accumulated `tot` of every mix variable
     for (const auto& s : c->steps) {
       switch (s.op) {
-        case OP_TRUE:
-          o << "  const E m" << nmx << " = emake(0u, 0u, 0u, 0u);\n";
-          nmx++;
-          break;
+        case OP_TRUE: {
+          Val z;
+          z.ext = true;
+          mixv.push_back(z);  // all four components constant 0
+        } break;
         case OP_AND_EQZ: {
-          std::string pw = pw_expr(c->mix_exp[s.a]);
-          std::string term = em.is_ext[s.b] ? "emul(" + pw + ", " + em.operand(s.b) + ")" : "emulf(" + pw + ", " + em.operand(s.b) + ")";
-          o << "  const E m" << nmx << " = eadd(m" << s.a << ", " << term << ");\n";
-          // Throttle: make the row offsets of the NEXT constraint's tap loads data-dependent on this constraint's
-          // accumulator (the compare is never true: field words are < P).  Without it the scheduler issues all ~400 tap
-          // loads of the straight-line program up front and spills their results.
-          if (++eqz_count % fence_every == 0) {
-            o << "  { const u32 dep = (m" << nmx << ".a == 0xffffffffu);";
-            for (unsigned b = 0; b <= max_back; b++) o << " ib" << b << " += dep;";
-            o << " }\n";
-          }
-          nmx++;
+          Val term = em.v_mul(pw_val(c->mix_exp[s.a]), em.use(s.b));
+          mixv.push_back(em.v_add(mixv[s.a], term, false));
         } break;
         case OP_AND_COND: {
-          std::string pw = pw_expr(c->mix_exp[s.a]);
-          std::string inner = em.is_ext[s.b] ? "emul(m" + std::to_string(s.c) + ", " + em.operand(s.b) + ")"
-                                             : "emulf(m" + std::to_string(s.c) + ", " + em.operand(s.b) + ")";
-          o << "  const E m" << nmx << " = eadd(m" << s.a << ", emul(" << inner << ", " << pw << "));\n";
-          nmx++;
+          Val inner = em.v_mul(mixv[s.c], em.use(s.b));
+          Val term = em.v_mul(inner, pw_val(c->mix_exp[s.a]));
+          mixv.push_back(em.v_add(mixv[s.a], term, false));
         } break;
-        default: em.step(o, s); break;
+        default: em.step(s); break;
       }
     }
+    o << "  const u32 iz = (i & 2) ? ((i & 1) ? iz3 : iz2) : ((i & 1) ? iz1 : iz0);\n";
+    Val r = em.v_mul(mixv[c->ret], Emitter::base(Emitter::named("iz")));
+    for (int k = 0; k < 4; k++) o << "  check[" << k << " * domain + i] = " << (r.ext || k == 0 ? r.c[k].str() : std::string("0u")) << ";\n";
+    o << "}\n\n";
   }
-  o << "  const u32 iz = (i & 2) ? ((i & 1) ? iz3 : iz2) : ((i & 1) ? iz1 : iz0);\n";
-  o << "  const E r = emulf(m" << c->ret << ", iz);\n";
-  o << "  check[i] = r.a; check[domain + i] = r.b; check[2 * domain + i] = r.c; check[3 * domain + i] = r.d;\n}\n\n";
   // ---- witgen: one thread per active trace row; taps read the trace domain (stride 1) ----
   o << "extern \"C\" __global__ void __launch_bounds__(256) b2z_witgen(const __grid_constant__ ColPtrs cp, "
        "const u32* __restrict__ globals, u64 mask, u64 active_rows) {\n";
   o << "  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;\n  if (i >= active_rows) return;\n";
   for (unsigned b = 0; b <= max_back; b++) o << "  const u32 ib" << b << " = (u32)((i - " << b << "ull) & mask) << 2;\n";
   {
-    Emitter em{c, true, {}, {}};
-    for (const auto& s : c->wit_steps) em.step(o, s);
-    for (size_t k = 0; k < c->wit_store_col.size(); k++)
-      o << "  const_cast<u32*>(cp.g2[" << c->wit_store_col[k] << "])[i] = " << em.operand(c->wit_store_var[k]) << ";\n";
+    Emitter em{c, true, &o, {}, 0};
+    for (const auto& s : c->wit_steps) em.step(s);
+    for (size_t k = 0; k < c->wit_store_col.size(); k++) {
+      Val v = em.use(c->wit_store_var[k]);
+      o << "  const_cast<u32*>(cp.g2[" << c->wit_store_col[k] << "])[i] = " << v.c[0].str() << ";\n";
+    }
   }
   o << "}\n";
   c->source = o.str();

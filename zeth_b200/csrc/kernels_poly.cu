@@ -345,16 +345,37 @@ __global__ void __launch_bounds__(PD_THREADS) poly_divide_local_kernel(const uin
   block_suffix_scan(sh, fp4_pow(z, PD_L), t, PD_THREADS);
   if (t == 0) st_ext(block_sums + 4 * (size_t)blockIdx.x, sh[0]);
 }
-// single block: carry[b] = sum_{b' > b} blocksum[b'] * zB^(b'-b-1), zB = z^(L*THREADS); remainder = carry[-1]
-__global__ void poly_divide_carry_kernel(const uint32_t* __restrict__ block_sums, uint32_t* __restrict__ carries, size_t nblocks, Fp4 zB,
-                                         uint32_t* __restrict__ remainder) {
-  if (threadIdx.x != 0) return;
-  Fp4 cur = fp4_zero();
-  for (size_t b = nblocks; b-- > 0;) {
-    st_ext(carries + 4 * b, cur);
-    cur = fp4_add(fp4_mul(cur, zB), ld_ext(block_sums + 4 * b));
+// single block: carry[b] = sum_{b' > b} blocksum[b'] * zB^(b'-b-1), zB = z^(L*THREADS); remainder = carry[-1].
+// Thread t owns the contiguous run of `per` block sums [t*per, (t+1)*per): local Horner, block-wide suffix scan with
+// multiplier zB^per, then a second walk over the run to emit the per-block carries.
+__global__ void __launch_bounds__(PD_THREADS) poly_divide_carry_kernel(const uint32_t* __restrict__ block_sums, uint32_t* __restrict__ carries,
+                                                                       size_t nblocks, Fp4 zB, uint32_t* __restrict__ remainder) {
+  __shared__ Fp4 sh[PD_THREADS];
+  const unsigned t = threadIdx.x;
+  const size_t per = (nblocks + PD_THREADS - 1) / PD_THREADS;
+  const size_t b0 = (size_t)t * per;
+  Fp4 acc = fp4_zero();  // sum_{b in run} blocksum[b] * zB^(b - b0)
+  for (size_t k = per; k-- > 0;) {
+    size_t b = b0 + k;
+    Fp4 v = b < nblocks ? ld_ext(block_sums + 4 * b) : fp4_zero();
+    acc = fp4_add(fp4_mul(acc, zB), v);
   }
-  st_ext(remainder, cur);
+  sh[t] = acc;
+  __syncthreads();
+  Fp4 zRun = fp4_pow(zB, per);
+  block_suffix_scan(sh, zRun, t, PD_THREADS);
+  // carry entering the top of this thread's run = suffix of the later runs
+  Fp4 cur = (t + 1 < PD_THREADS) ? sh[t + 1] : fp4_zero();
+  for (size_t k = per; k-- > 0;) {
+    size_t b = b0 + k;
+    if (b < nblocks) {
+      st_ext(carries + 4 * b, cur);
+      cur = fp4_add(fp4_mul(cur, zB), ld_ext(block_sums + 4 * b));
+    } else {
+      cur = fp4_mul(cur, zB);
+    }
+  }
+  if (t == 0) st_ext(remainder, cur);
 }
 __global__ void __launch_bounds__(PD_THREADS) poly_divide_apply_kernel(uint32_t* __restrict__ p, size_t count, Fp4 z,
                                                                        const uint32_t* __restrict__ carries) {
@@ -395,7 +416,7 @@ b2z_err launch_poly_divide(b2z_ctx* ctx, uint32_t* ext_coeffs, size_t count, con
   uint32_t* sums = tmp;
   uint32_t* carries = tmp + 4 * nblocks;
   poly_divide_local_kernel<<<(unsigned)nblocks, PD_THREADS, 0, ctx->stream>>>(ext_coeffs, count, z, sums);
-  poly_divide_carry_kernel<<<1, 32, 0, ctx->stream>>>(sums, carries, nblocks, fp4_pow(z, per_block), remainder_dev);
+  poly_divide_carry_kernel<<<1, PD_THREADS, 0, ctx->stream>>>(sums, carries, nblocks, fp4_pow(z, per_block), remainder_dev);
   poly_divide_apply_kernel<<<(unsigned)nblocks, PD_THREADS, 0, ctx->stream>>>(ext_coeffs, count, z, carries);
   ctx->launches += 3;
   B2Z_CUDA(cudaGetLastError());
