@@ -23,7 +23,7 @@ static b2z_err upload_consts(b2z_ctx* ctx) {
 }
 
 __global__ void __launch_bounds__(128) hash_rows_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ matrix, size_t rows,
-                                                        size_t cols) {
+                                                        size_t cols, uint32_t ones) {
   size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (r >= rows) return;
   uint32_t s[P2_CELLS];
@@ -34,26 +34,26 @@ __global__ void __launch_bounds__(128) hash_rows_kernel(uint32_t* __restrict__ o
   for (size_t blk = 0; blk < full; blk++) {
 #pragma unroll
     for (int i = 0; i < P2_RATE; i++) s[i] = __ldg(p + (blk * P2_RATE + i) * rows);
-    p2_permute_dev(s, c_p2);
+    p2_permute_dev(s, c_p2, ones);
   }
   size_t rem = cols - full * P2_RATE;
   if (rem != 0 || cols == 0) {
 #pragma unroll
     for (int i = 0; i < P2_RATE; i++) s[i] = (size_t)i < rem ? __ldg(p + (full * P2_RATE + i) * rows) : 0u;
-    p2_permute_dev(s, c_p2);
+    p2_permute_dev(s, c_p2, ones);
   }
   uint4* o = reinterpret_cast<uint4*>(out + 8 * r);
   o[0] = make_uint4(s[0], s[1], s[2], s[3]);
   o[1] = make_uint4(s[4], s[5], s[6], s[7]);
 }
 
-__global__ void __launch_bounds__(128) hash_fold_kernel(uint32_t* __restrict__ nodes, size_t in_size, size_t out_size) {
+__global__ void __launch_bounds__(128) hash_fold_kernel(uint32_t* __restrict__ nodes, size_t in_size, size_t out_size, uint32_t ones) {
   size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (j >= out_size) return;
   const uint4* in = reinterpret_cast<const uint4*>(nodes + 8 * (in_size + 2 * j));
   uint4 a = in[0], b = in[1], c = in[2], d = in[3];
   uint32_t s[P2_CELLS] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w, 0, 0, 0, 0, 0, 0, 0, 0};
-  p2_permute_dev(s, c_p2);
+  p2_permute_dev(s, c_p2, ones);
   uint4* o = reinterpret_cast<uint4*>(nodes + 8 * (out_size + j));
   o[0] = make_uint4(s[0], s[1], s[2], s[3]);
   o[1] = make_uint4(s[4], s[5], s[6], s[7]);
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(128) hash_fold_kernel(uint32_t* __restrict__ n
 b2z_err launch_hash_rows(b2z_ctx* ctx, uint32_t* out, const uint32_t* matrix, size_t rows, size_t cols) {
   if (rows == 0) return nullptr;
   B2Z_TRY(upload_consts(ctx));
-  hash_rows_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, ctx->stream>>>(out, matrix, rows, cols);
+  hash_rows_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, ctx->stream>>>(out, matrix, rows, cols, 0xffffffffu);
   ctx->launches++;
   B2Z_CUDA(cudaGetLastError());
   return nullptr;
@@ -71,7 +71,7 @@ b2z_err launch_hash_rows(b2z_ctx* ctx, uint32_t* out, const uint32_t* matrix, si
 b2z_err launch_hash_fold(b2z_ctx* ctx, uint32_t* nodes, size_t in_size, size_t out_size) {
   if (out_size == 0) return nullptr;
   B2Z_TRY(upload_consts(ctx));
-  hash_fold_kernel<<<(unsigned)((out_size + 127) / 128), 128, 0, ctx->stream>>>(nodes, in_size, out_size);
+  hash_fold_kernel<<<(unsigned)((out_size + 127) / 128), 128, 0, ctx->stream>>>(nodes, in_size, out_size, 0xffffffffu);
   ctx->launches++;
   B2Z_CUDA(cudaGetLastError());
   return nullptr;

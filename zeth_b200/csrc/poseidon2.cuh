@@ -80,20 +80,29 @@ B2Z_HD void p2_m_int(uint32_t* s, const uint32_t* diag) {
 
 #if defined(__CUDACC__)
 // ---- device-tuned variants (same canonical results; see DESIGN.md "Poseidon2 instruction budget") ----
+// Pipe pinning.  The Montgomery products saturate the FMA pipe (IMAD.WIDE / IMAD.HI take ~2 issue slots each:
+// tools/microbench/intpipe.cu), yet ptxas balances pipes by instruction COUNT and re-encodes about a quarter of the
+// plain adds as IMAD.IADD on that same pipe.  `__viaddmin_u32(a, b, ones)` = min(a + b, 0xffffffff) = a + b is a single
+// VIADDMNMX, which only exists on the ALU pipe; `ones` is a run-time all-ones kernel argument so it cannot be folded.
+__device__ __forceinline__ uint32_t add_alu(uint32_t a, uint32_t b, uint32_t ones) { return __viaddmin_u32(a, b, ones); }
+__device__ __forceinline__ uint32_t fp_add_p(uint32_t a, uint32_t b, uint32_t ones) {
+  uint32_t r = add_alu(a, b, ones);
+  return umin32(r, r - P);
+}
 // Signed-redundant Montgomery product: inputs in (-P, P) as int32, output in (-P, P); no final correction.
-__device__ __forceinline__ int32_t fp_mul_s(int32_t a, int32_t b) {
+__device__ __forceinline__ int32_t fp_mul_s(int32_t a, int32_t b, uint32_t ones) {
   int64_t t = (int64_t)a * b;
   uint32_t m = (uint32_t)t * MONT_PINV;
   int32_t u = __mulhi((int32_t)m, (int32_t)P);
-  return (int32_t)(t >> 32) - u;
+  return (int32_t)add_alu((uint32_t)(t >> 32), 0u - (uint32_t)u, ones);
 }
 // x^7 of (s + rc): one raw add (rc - P keeps the sum inside (-P, P)), four uncorrected products, one final correction
-__device__ __forceinline__ uint32_t p2_sbox_rc(uint32_t s, int32_t rc_minus_p) {
-  int32_t x = (int32_t)s + rc_minus_p;
-  int32_t x2 = fp_mul_s(x, x);
-  int32_t x3 = fp_mul_s(x2, x);
-  int32_t x4 = fp_mul_s(x2, x2);
-  uint32_t x7 = (uint32_t)fp_mul_s(x3, x4);
+__device__ __forceinline__ uint32_t p2_sbox_rc(uint32_t s, int32_t rc_minus_p, uint32_t ones) {
+  int32_t x = (int32_t)add_alu(s, (uint32_t)rc_minus_p, ones);
+  int32_t x2 = fp_mul_s(x, x, ones);
+  int32_t x3 = fp_mul_s(x2, x, ones);
+  int32_t x4 = fp_mul_s(x2, x2, ones);
+  uint32_t x7 = (uint32_t)fp_mul_s(x3, x4, ones);
   return umin32(x7, x7 + P);
 }
 // Shoup product by a constant: x * d mod P with dp = floor(d * 2^32 / P); x canonical, result canonical
@@ -102,32 +111,66 @@ __device__ __forceinline__ uint32_t fp_mul_shoup(uint32_t x, uint32_t d, uint32_
   uint32_t r = x * d - q * P;
   return umin32(r, r - P);
 }
-__device__ __forceinline__ void p2_m_int_dev(uint32_t* s, const P2Consts& k) {
-  uint32_t tot = 0;
+__device__ __forceinline__ void p2_m_ext_dev(uint32_t* s, uint32_t ones) {
 #pragma unroll
-  for (int i = 0; i < P2_CELLS; i++) tot = fp_add(tot, s[i]);
+  for (int c = 0; c < P2_CELLS; c += 4) {
+    uint32_t a = s[c], b = s[c + 1], cc = s[c + 2], d = s[c + 3];
+    uint32_t t0 = fp_add_p(a, b, ones);
+    uint32_t t1 = fp_add_p(cc, d, ones);
+    uint32_t t2 = fp_add_p(fp_add_p(b, b, ones), t1, ones);
+    uint32_t t3 = fp_add_p(fp_add_p(d, d, ones), t0, ones);
+    uint32_t t1x2 = fp_add_p(t1, t1, ones);
+    uint32_t t4 = fp_add_p(fp_add_p(t1x2, t1x2, ones), t3, ones);
+    uint32_t t0x2 = fp_add_p(t0, t0, ones);
+    uint32_t t5 = fp_add_p(fp_add_p(t0x2, t0x2, ones), t2, ones);
+    s[c] = fp_add_p(t3, t5, ones);
+    s[c + 1] = t5;
+    s[c + 2] = fp_add_p(t2, t4, ones);
+    s[c + 3] = t4;
+  }
+  uint32_t sum0 = s[0], sum1 = s[1], sum2 = s[2], sum3 = s[3];
 #pragma unroll
-  for (int i = 0; i < P2_CELLS; i++) s[i] = fp_add(tot, fp_mul_shoup(s[i], k.diag_canon[i], k.diag_shoup[i]));
+  for (int c = 4; c < P2_CELLS; c += 4) {
+    sum0 = fp_add_p(sum0, s[c], ones);
+    sum1 = fp_add_p(sum1, s[c + 1], ones);
+    sum2 = fp_add_p(sum2, s[c + 2], ones);
+    sum3 = fp_add_p(sum3, s[c + 3], ones);
+  }
+#pragma unroll
+  for (int c = 0; c < P2_CELLS; c += 4) {
+    s[c] = fp_add_p(s[c], sum0, ones);
+    s[c + 1] = fp_add_p(s[c + 1], sum1, ones);
+    s[c + 2] = fp_add_p(s[c + 2], sum2, ones);
+    s[c + 3] = fp_add_p(s[c + 3], sum3, ones);
+  }
 }
-__device__ __forceinline__ void p2_permute_dev(uint32_t* s, const P2Consts& k) {
+__device__ __forceinline__ void p2_m_int_dev(uint32_t* s, const P2Consts& k, uint32_t ones) {
+  uint32_t tot = s[0];
+#pragma unroll
+  for (int i = 1; i < P2_CELLS; i++) tot = fp_add_p(tot, s[i], ones);
+#pragma unroll
+  for (int i = 0; i < P2_CELLS; i++) s[i] = fp_add_p(tot, fp_mul_shoup(s[i], k.diag_canon[i], k.diag_shoup[i]), ones);
+}
+// `ones` must be 0xffffffff at run time (a kernel argument the compiler cannot fold)
+__device__ __forceinline__ void p2_permute_dev(uint32_t* s, const P2Consts& k, uint32_t ones) {
   const int32_t* rc = k.rc_minus_p;
-  p2_m_ext(s);
+  p2_m_ext_dev(s, ones);
   for (int r = 0; r < P2_ROUNDS_HALF_FULL; r++) {
 #pragma unroll
-    for (int i = 0; i < P2_CELLS; i++) s[i] = p2_sbox_rc(s[i], rc[i]);
+    for (int i = 0; i < P2_CELLS; i++) s[i] = p2_sbox_rc(s[i], rc[i], ones);
     rc += P2_CELLS;
-    p2_m_ext(s);
+    p2_m_ext_dev(s, ones);
   }
   for (int r = 0; r < P2_ROUNDS_PARTIAL; r++) {
-    s[0] = p2_sbox_rc(s[0], rc[0]);
+    s[0] = p2_sbox_rc(s[0], rc[0], ones);
     rc += 1;
-    p2_m_int_dev(s, k);
+    p2_m_int_dev(s, k, ones);
   }
   for (int r = 0; r < P2_ROUNDS_HALF_FULL; r++) {
 #pragma unroll
-    for (int i = 0; i < P2_CELLS; i++) s[i] = p2_sbox_rc(s[i], rc[i]);
+    for (int i = 0; i < P2_CELLS; i++) s[i] = p2_sbox_rc(s[i], rc[i], ones);
     rc += P2_CELLS;
-    p2_m_ext(s);
+    p2_m_ext_dev(s, ones);
   }
 }
 #endif
