@@ -118,3 +118,28 @@ def test_full_gpu_pipeline_witgen_to_seal(hal, oracle):
     assert np.array_equal(glob, oglob)
     assert np.array_equal(seal, oc.prove(po2, code, data, oglob, noise, zk))
     c.close()
+
+
+@pytest.mark.parametrize("po2", [20, 22])
+def test_baseline_size_segments_verify(hal, po2):
+    """BASELINE.json sizes (po2 = 20 and 22, W = 256): the oracle is too slow here, so use the size-independent
+    property -- a seal produced from a GPU-generated valid witness must be accepted by the host verifier, must have the
+    layout-determined length, and one flipped word must be rejected."""
+    sc = S.circuit_planning()
+    n = 1 << po2
+    zk = 1994
+    wa, wc, wd = sc.group_sizes
+    c = H.Circuit(hal, sc.blob)
+    dcode, ddata = hal.alloc(wc * n), hal.alloc(wd * n)
+    dglob, dnoise = hal.alloc(sc.globals_size), hal.alloc(wa * zk)
+    hal.witgen(c, po2, dcode, ddata, dglob, dnoise, 0xB2000002, zk)
+    glob = hal.view(dglob, sc.globals_size)
+    seal = hal.prove_segment_device(c, po2, dcode, ddata, glob, dnoise, zk)
+    assert seal.size == c.seal_words(po2)
+    assert c.verify(seal) == 0
+    bad = seal.copy()
+    bad[seal.size - 7] ^= 2
+    assert c.verify(bad) != 0
+    for p in (dcode, ddata, dglob, dnoise):
+        hal.free(p)
+    c.close()

@@ -5,6 +5,8 @@
 // scope rows a9/a10).  One thread owns one row (or one parent node): the 24-word state stays in registers, loads
 // are coalesced across the warp because consecutive threads read consecutive rows of the same column.
 // These kernels are INT32-ALU bound (1 356 modular multiplies per 64 bytes absorbed), not HBM bound.
+#include <mutex>
+
 #include "common.h"
 #include "poseidon2.cuh"
 #include "poseidon2_consts.h"
@@ -15,6 +17,8 @@ __constant__ P2Consts c_p2;
 static bool g_p2_uploaded[16] = {};
 
 static b2z_err upload_consts(b2z_ctx* ctx) {
+  static std::mutex m;
+  std::lock_guard<std::mutex> lock(m);
   if (ctx->device < 16 && g_p2_uploaded[ctx->device]) return nullptr;
   const P2Consts& h = p2_host_consts();
   B2Z_CUDA(cudaMemcpyToSymbol(c_p2, &h, sizeof(P2Consts), 0, cudaMemcpyHostToDevice));

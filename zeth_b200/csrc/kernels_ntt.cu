@@ -16,6 +16,7 @@
 // Columns are processed in chunks sized to stay inside the 126 MB L2, so that the passes after the first one read and
 // write L2-resident lines and HBM sees close to the compulsory traffic (1 read of the input, 1 write of the output).
 #include <map>
+#include <mutex>
 #include <tuple>
 
 #include "common.h"
@@ -47,9 +48,11 @@ struct TwistKey {
 struct NttTables {
   std::map<TwistKey, uint32_t*> twist;
 };
-static std::map<b2z_ctx*, NttTables> g_tables;  // one context per thread (see b2z.h); guarded by that contract
+static std::map<b2z_ctx*, NttTables> g_tables;  // contexts are single-threaded, the registry itself is shared
+static std::mutex g_tables_mutex;
 
 static b2z_err get_twist(b2z_ctx* ctx, unsigned a, unsigned b, bool inv, const uint32_t** out) {
+  std::lock_guard<std::mutex> lock(g_tables_mutex);
   NttTables& t = g_tables[ctx];
   TwistKey k{a, b, inv};
   auto it = t.twist.find(k);
@@ -67,6 +70,7 @@ static b2z_err get_twist(b2z_ctx* ctx, unsigned a, unsigned b, bool inv, const u
   return nullptr;
 }
 void ntt_release_tables(b2z_ctx* ctx) {
+  std::lock_guard<std::mutex> lock(g_tables_mutex);
   auto it = g_tables.find(ctx);
   if (it == g_tables.end()) return;
   for (auto& kv : it->second.twist) cudaFree(kv.second);
@@ -75,6 +79,8 @@ void ntt_release_tables(b2z_ctx* ctx) {
 
 b2z_err ensure_tables(b2z_ctx* ctx, unsigned po2, bool, bool, bool pow3) {
   B2Z_REQUIRE(po2 <= MAX_PO2, "transform size exceeds 2^26");
+  static std::mutex w16_mutex;
+  std::lock_guard<std::mutex> w16_lock(w16_mutex);
   if (ctx->device < 16 && !g_w16_uploaded[ctx->device]) {
     uint32_t w[8], wi[8], g = rou_fwd(4), gi = rou_rev(4);
     w[0] = wi[0] = MONT_ONE;
