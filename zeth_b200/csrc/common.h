@@ -60,7 +60,8 @@ namespace b2z {
 
 // ---- kernel launchers (kernels_*.cu); all enqueue on ctx->stream and bump ctx->launches ----
 b2z_err ensure_tables(b2z_ctx* ctx, unsigned po2, bool fwd, bool rev, bool pow3);
-b2z_err launch_interpolate(b2z_ctx* ctx, uint32_t* io, size_t count, unsigned po2, bool fuse_zk_shift);
+// `src` (optional): read the natural-order evaluations from a separate buffer (saves the witness -> coefficient copy)
+b2z_err launch_interpolate(b2z_ctx* ctx, uint32_t* io, size_t count, unsigned po2, bool fuse_zk_shift, const uint32_t* src = nullptr);
 b2z_err launch_evaluate(b2z_ctx* ctx, uint32_t* out, const uint32_t* in, size_t count, unsigned out_po2, unsigned expand_bits);
 b2z_err launch_bit_reverse(b2z_ctx* ctx, uint32_t* io, size_t count, unsigned po2);
 b2z_err launch_zk_shift(b2z_ctx* ctx, uint32_t* io, size_t count, unsigned po2);
@@ -73,6 +74,8 @@ b2z_err launch_evaluate_any_host(b2z_ctx* ctx, const uint32_t* coeffs, unsigned 
                                  size_t eval_count, uint32_t* out);
 b2z_err launch_mix_poly_coeffs(b2z_ctx* ctx, uint32_t* out, const Fp4& mix_start, const Fp4& mix, const uint32_t* in,
                                const uint32_t* combos_dev, size_t input_size, size_t count);
+b2z_err launch_mix_poly_coeffs_host(b2z_ctx* ctx, uint32_t* out, const Fp4& mix_start, const Fp4& mix, const uint32_t* in,
+                                    const uint32_t* combos_host, size_t input_size, size_t count);
 b2z_err launch_add_elem(b2z_ctx* ctx, uint32_t* out, const uint32_t* a, const uint32_t* b, size_t n);
 b2z_err launch_sum_extelem(b2z_ctx* ctx, uint32_t* out, const uint32_t* in, size_t count, size_t to_add);
 b2z_err launch_zeroize(b2z_ctx* ctx, uint32_t* io, size_t n);

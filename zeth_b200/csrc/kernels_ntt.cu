@@ -447,11 +447,15 @@ b2z_err launch_evaluate(b2z_ctx* ctx, uint32_t* out, const uint32_t* in, size_t 
   return nullptr;
 }
 
-b2z_err launch_interpolate(b2z_ctx* ctx, uint32_t* io, size_t count, unsigned po2, bool fuse_zk_shift) {
+b2z_err launch_interpolate(b2z_ctx* ctx, uint32_t* io, size_t count, unsigned po2, bool fuse_zk_shift, const uint32_t* src) {
   if (count == 0) return nullptr;
+  if (src == io) src = nullptr;
   B2Z_TRY(ensure_tables(ctx, po2, false, false, fuse_zk_shift));
   const unsigned logn = po2;
-  if (logn == 0) return nullptr;
+  if (logn == 0) {
+    if (src) B2Z_CUDA(cudaMemcpyAsync(io, src, 4 * count, cudaMemcpyDeviceToDevice, ctx->stream));
+    return nullptr;
+  }
   uint32_t norm = fp_inv(fp_from_u32((uint32_t)(((uint64_t)1 << po2) % P)));
   unsigned R[8], np = 0;
   plan_passes(logn, R, &np);
@@ -473,7 +477,7 @@ b2z_err launch_interpolate(b2z_ctx* ctx, uint32_t* io, size_t count, unsigned po
     for (unsigned kk = np; kk-- > 0;) {
       PassArgs a{};
       a.out = io + c0 * n;
-      a.in = io + c0 * n;
+      a.in = (src && kk == np - 1) ? src + c0 * n : io + c0 * n;
       a.pass_twist = pass_tw[kk];
       a.group_twist = grp_tw[kk];
       a.scale_tab = (kk == 0 && fuse_zk_shift) ? ctx->pow3rev[po2] : nullptr;

@@ -4,6 +4,8 @@
 // Semantics: risc0-zkp 3.0.2 hal/cpu.rs (fri_fold, batch_evaluate_any, mix_poly_coeffs, eltwise_*, gather_sample),
 // core/poly.rs poly_divide and prove/merkle.rs MerkleTreeProver::prove (rows a13-a16).
 // All of these are HBM-bandwidth bound: one coalesced read of the inputs, ext-field arithmetic in registers.
+#include <algorithm>
+
 #include "common.h"
 
 namespace b2z {
@@ -196,56 +198,77 @@ __global__ void mix_pow_table_kernel(uint32_t* tab, Fp4 start, Fp4 mix, size_t n
     cur = fp4_mul(cur, mix);
   }
 }
+// Columns are visited in combo order (order[] = column indices sorted by combo id, seg[k]..seg[k+1] = the columns of the
+// k-th combo of this launch), so the inner loop is branch-free and each accumulator is a plain register.
+struct MpcSegs {
+  uint32_t combo[MPC_MAX_COMBOS];    // output combo id of slot k
+  uint32_t seg[MPC_MAX_COMBOS + 1];  // range of order[] belonging to slot k
+  uint32_t n;                        // slots used
+};
 __global__ void __launch_bounds__(256) mix_poly_coeffs_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ pows,
-                                                              const uint32_t* __restrict__ in, const uint32_t* __restrict__ combos,
-                                                              size_t input_size, size_t count, unsigned combo_lo, unsigned combo_hi) {
+                                                              const uint32_t* __restrict__ in, const uint32_t* __restrict__ order,
+                                                              size_t count, MpcSegs segs) {
   size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (idx >= count) return;
-  Fp4 acc[MPC_MAX_COMBOS];
-#pragma unroll
-  for (int k = 0; k < MPC_MAX_COMBOS; k++) acc[k] = fp4_zero();
-  for (size_t i = 0; i < input_size; i++) {
-    unsigned cid = combos[i];
-    if (cid < combo_lo || cid >= combo_hi) continue;
-    uint32_t v = __ldg(in + i * count + idx);
-    const uint4 pw = *reinterpret_cast<const uint4*>(pows + 4 * i);
-    Fp4 term = fp4_make(fp_mul(pw.x, v), fp_mul(pw.y, v), fp_mul(pw.z, v), fp_mul(pw.w, v));
-    unsigned slot = cid - combo_lo;
-#pragma unroll
-    for (int k = 0; k < MPC_MAX_COMBOS; k++)
-      if ((unsigned)k == slot) acc[k] = fp4_add(acc[k], term);
-  }
-#pragma unroll
-  for (int k = 0; k < MPC_MAX_COMBOS; k++) {
-    if (combo_lo + k >= combo_hi) break;
-    uint4* o = reinterpret_cast<uint4*>(out + 4 * ((size_t)(combo_lo + k) * count + idx));
+#pragma unroll 1
+  for (unsigned k = 0; k < segs.n; k++) {
+    Fp4 acc = fp4_zero();
+    for (unsigned j = segs.seg[k]; j < segs.seg[k + 1]; j++) {
+      unsigned i = order[j];
+      uint32_t v = __ldg(in + (size_t)i * count + idx);
+      const uint4 pw = *reinterpret_cast<const uint4*>(pows + 4 * (size_t)i);
+      acc.e[0] = fp_add(acc.e[0], fp_mul(pw.x, v));
+      acc.e[1] = fp_add(acc.e[1], fp_mul(pw.y, v));
+      acc.e[2] = fp_add(acc.e[2], fp_mul(pw.z, v));
+      acc.e[3] = fp_add(acc.e[3], fp_mul(pw.w, v));
+    }
+    uint4* o = reinterpret_cast<uint4*>(out + 4 * ((size_t)segs.combo[k] * count + idx));
     uint4 cur = *o;
-    Fp4 r = fp4_add(fp4_make(cur.x, cur.y, cur.z, cur.w), acc[k]);
+    Fp4 r = fp4_add(fp4_make(cur.x, cur.y, cur.z, cur.w), acc);
     *o = make_uint4(r.e[0], r.e[1], r.e[2], r.e[3]);
   }
 }
-b2z_err launch_mix_poly_coeffs(b2z_ctx* ctx, uint32_t* out, const Fp4& mix_start, const Fp4& mix, const uint32_t* in,
-                               const uint32_t* combos_dev, size_t input_size, size_t count) {
+b2z_err launch_mix_poly_coeffs_host(b2z_ctx* ctx, uint32_t* out, const Fp4& mix_start, const Fp4& mix, const uint32_t* in,
+                                    const uint32_t* combos_host, size_t input_size, size_t count) {
   if (!input_size || !count) return nullptr;
-  // combo id range (host needs it to size the register accumulators): fetch the ids (small) synchronously
-  std::vector<uint32_t> ids(input_size);
-  B2Z_CUDA(cudaMemcpyAsync(ids.data(), combos_dev, 4 * input_size, cudaMemcpyDeviceToHost, ctx->stream));
-  B2Z_CUDA(cudaStreamSynchronize(ctx->stream));
-  uint32_t lo = ids[0], hi = ids[0];
-  for (uint32_t v : ids) { lo = v < lo ? v : lo; hi = v > hi ? v : hi; }
-  uint32_t* pows = nullptr;
+  // column order sorted by combo id (stable), split into launches of at most MPC_MAX_COMBOS distinct combos
+  std::vector<uint32_t> order(input_size);
+  for (size_t i = 0; i < input_size; i++) order[i] = (uint32_t)i;
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return combos_host[a] < combos_host[b]; });
+  uint32_t *pows = nullptr, *order_dev = nullptr;
   B2Z_CUDA(cudaMallocAsync(&pows, 16 * input_size, ctx->stream));
+  B2Z_CUDA(cudaMallocAsync(&order_dev, 4 * input_size, ctx->stream));
+  B2Z_CUDA(cudaMemcpyAsync(order_dev, order.data(), 4 * input_size, cudaMemcpyHostToDevice, ctx->stream));
   size_t tthreads = (input_size + 63) / 64;
   mix_pow_table_kernel<<<(unsigned)((tthreads + 63) / 64), 64, 0, ctx->stream>>>(pows, mix_start, mix, input_size);
   ctx->launches++;
-  for (uint32_t c0 = lo; c0 <= hi; c0 += MPC_MAX_COMBOS) {
-    uint32_t c1 = c0 + MPC_MAX_COMBOS < hi + 1 ? c0 + MPC_MAX_COMBOS : hi + 1;
-    mix_poly_coeffs_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(out, pows, in, combos_dev, input_size, count, c0, c1);
+  size_t j = 0;
+  while (j < input_size) {
+    MpcSegs segs{};
+    while (j < input_size && segs.n < MPC_MAX_COMBOS) {
+      uint32_t cid = combos_host[order[j]];
+      segs.combo[segs.n] = cid;
+      segs.seg[segs.n] = (uint32_t)j;
+      while (j < input_size && combos_host[order[j]] == cid) j++;
+      segs.n++;
+      segs.seg[segs.n] = (uint32_t)j;
+    }
+    mix_poly_coeffs_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(out, pows, in, order_dev, count, segs);
     ctx->launches++;
   }
   B2Z_CUDA(cudaGetLastError());
   B2Z_CUDA(cudaFreeAsync(pows, ctx->stream));
+  B2Z_CUDA(cudaFreeAsync(order_dev, ctx->stream));
   return nullptr;
+}
+// device-array form of the C ABI: fetch the (small) combo-id array
+b2z_err launch_mix_poly_coeffs(b2z_ctx* ctx, uint32_t* out, const Fp4& mix_start, const Fp4& mix, const uint32_t* in,
+                               const uint32_t* combos_dev, size_t input_size, size_t count) {
+  if (!input_size || !count) return nullptr;
+  std::vector<uint32_t> ids(input_size);
+  B2Z_CUDA(cudaMemcpyAsync(ids.data(), combos_dev, 4 * input_size, cudaMemcpyDeviceToHost, ctx->stream));
+  B2Z_CUDA(cudaStreamSynchronize(ctx->stream));
+  return launch_mix_poly_coeffs_host(ctx, out, mix_start, mix, in, ids.data(), input_size, count);
 }
 
 // ---------------- element-wise ----------------

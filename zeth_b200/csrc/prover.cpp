@@ -164,8 +164,8 @@ static b2z_err commit_group(b2z_ctx* ctx, DevMem& mem, PolyGroupDev& pg, const u
   for (size_t c0 = 0, k = 0; c0 < count; c0 += chunk_cols, k++) {
     size_t cols = count - c0 < chunk_cols ? count - c0 : chunk_cols;
     if (chunk_events && k < chunk_events->size()) B2Z_CUDA(cudaStreamWaitEvent(ctx->stream, (*chunk_events)[k], 0));
-    B2Z_CUDA(cudaMemcpyAsync(coeffs + c0 * n, witness + c0 * n, 4 * cols * n, cudaMemcpyDeviceToDevice, ctx->stream));
-    B2Z_TRY(launch_interpolate(ctx, coeffs + c0 * n, cols, po2, /*fuse_zk_shift=*/true));
+    // the first inverse pass reads the witness directly and writes the coefficient buffer (no separate copy)
+    B2Z_TRY(launch_interpolate(ctx, coeffs + c0 * n, cols, po2, /*fuse_zk_shift=*/true, witness + c0 * n));
     B2Z_TRY(launch_evaluate(ctx, pg.evaluated + c0 * domain, coeffs + c0 * n, cols, po2 + 2, 2));
   }
   return poly_group_finish(ctx, mem, pg, po2, seal, rng);
@@ -332,22 +332,19 @@ b2z_err prove_segment_device(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, c
   B2Z_TRY(mem.alloc(&combos, 4 * n * (n_combos + 1)));
   B2Z_CUDA(cudaMemsetAsync(combos, 0, 16 * n * (n_combos + 1), ctx->stream));
   {
-    // combo id of every column, device-resident
+    // combo id of every column (host side: the launcher sorts the columns by combo)
     std::vector<uint32_t> ids(n_regs + B2Z_CHECK_SIZE);
     for (size_t r = 0; r < n_regs; r++) ids[r] = c->reg_combo[r];
     for (size_t i = 0; i < B2Z_CHECK_SIZE; i++) ids[n_regs + i] = (uint32_t)n_combos;
-    uint32_t* ids_dev = nullptr;
-    B2Z_TRY(mem.alloc(&ids_dev, ids.size()));
-    B2Z_CUDA(cudaMemcpyAsync(ids_dev, ids.data(), 4 * ids.size(), cudaMemcpyHostToDevice, ctx->stream));
     Fp4 cur_mix = fp4_one();
     size_t r = 0;
     for (int g = 0; g < 3; g++) {
       size_t gs = c->group_size[g];
-      B2Z_TRY(launch_mix_poly_coeffs(ctx, combos, cur_mix, mixv, pg[g].coeffs, ids_dev + r, gs, n));
+      B2Z_TRY(launch_mix_poly_coeffs_host(ctx, combos, cur_mix, mixv, pg[g].coeffs, ids.data() + r, gs, n));
       cur_mix = fp4_mul(cur_mix, fp4_pow(mixv, gs));
       r += gs;
     }
-    B2Z_TRY(launch_mix_poly_coeffs(ctx, combos, cur_mix, mixv, check_pg.coeffs, ids_dev + n_regs, B2Z_CHECK_SIZE, n));
+    B2Z_TRY(launch_mix_poly_coeffs_host(ctx, combos, cur_mix, mixv, check_pg.coeffs, ids.data() + n_regs, B2Z_CHECK_SIZE, n));
   }
   {
     // U polynomials per combo (same sums the verifier forms as combo_u), subtracted from the low coefficients
