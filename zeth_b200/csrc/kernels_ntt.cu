@@ -15,6 +15,8 @@
 //     3^rev(j) into the last inverse pass's stores.
 // Columns are processed in chunks sized to stay inside the 126 MB L2, so that the passes after the first one read and
 // write L2-resident lines and HBM sees close to the compulsory traffic (1 read of the input, 1 write of the output).
+#include <cuda.h>  // CUtensorMap types only; the encoder is fetched with cudaGetDriverEntryPoint (no libcuda link)
+
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -102,6 +104,45 @@ b2z_err ensure_tables(b2z_ctx* ctx, unsigned po2, bool, bool, bool pow3) {
   return nullptr;
 }
 
+
+// ---- TMA (cp.async.bulk.tensor) staging of strided tiles ----
+// A strided pass tile is a box {32 adjacent positions, 2^R points at stride 2^s_lo, 1 block} of the 3-D view
+// [total / 2^(s_lo+R)][2^R][2^s_lo] of the column buffer; one elected thread issues the bulk tensor copy, the tile lands in
+// shared memory as dense [point][lane] (exactly the compute layout) and completion is signalled on an mbarrier.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+               "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"((uint64_t)map), "r"(smem_u32(src)), "r"(c0),
+               "r"(c1), "r"(c2)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 // ---- register-level radix-2^Q butterflies with constant sixteenth-root twiddles ----
 // forward: decimation in time, layers FIRST..Q (in place; positions hold the bit-reversed-order input)
 template <int Q, int FIRST>
@@ -145,8 +186,13 @@ __device__ __forceinline__ void dif_base(uint32_t* v) {
 // One radix group over bits [G_LO, G_LO + Q) of the R-bit point index, for all lanes of the tile.
 //   smem address of (point p, lane l) = p * PITCH_P + l * PITCH_L  (all compile-time, so every access is base + immediate)
 //   intra-pass twist (warp-uniform, staged in shared memory): multiply point p by tws[p] after (forward) / before (inverse)
-template <int R, int Q, int G_LO, bool ROWS, bool INV, int FIRST, bool TWIST>
-__device__ __forceinline__ void radix_group(uint32_t* sm, const uint32_t* tws, unsigned lane, unsigned warp, unsigned nwarps) {
+// PTW: additionally apply the inter-pass twist here (TMA path: the tile arrives untouched in shared memory, so the twist
+//      moves from the tile load/store loops into the first-executed / last-executed radix group); `ptw` points at the
+//      table entry of (point 0, this lane), consecutive points are `pstride` entries apart, `pmask` wraps the period.
+template <int R, int Q, int G_LO, bool ROWS, bool INV, int FIRST, bool TWIST, bool PTW = false>
+__device__ __forceinline__ void radix_group(uint32_t* sm, const uint32_t* tws, unsigned lane, unsigned warp, unsigned nwarps,
+                                            const uint32_t* __restrict__ ptab = nullptr, uint32_t pbase = 0, uint32_t pstride = 0,
+                                            uint32_t pmask = 0) {
   constexpr unsigned PITCH_P = ROWS ? 1u : 32u;
   constexpr unsigned PITCH_L = ROWS ? ((1u << R) + 1u) : 1u;
   constexpr unsigned SETS = 1u << (R - Q);
@@ -157,9 +203,15 @@ __device__ __forceinline__ void radix_group(uint32_t* sm, const uint32_t* tws, u
     const unsigned p0 = (high << (G_LO + Q)) | low;
     uint32_t* base = lane_base + p0 * PITCH_P;
     uint32_t v[1 << Q];
+    uint32_t pt[PTW ? (1 << Q) : 1];
+    if (PTW) {
+#pragma unroll
+      for (int j = 0; j < (1 << Q); j++) pt[j] = __ldg(ptab + ((pbase + (p0 + (j << G_LO)) * pstride) & pmask));
+    }
 #pragma unroll
     for (int j = 0; j < (1 << Q); j++) {
       uint32_t x = base[(j << G_LO) * PITCH_P];
+      if (PTW && !INV) x = fp_mul(x, pt[j]);
       if (INV && TWIST) x = fp_mul(x, tws[p0 + (j << G_LO)]);
       v[j] = x;
     }
@@ -169,6 +221,7 @@ __device__ __forceinline__ void radix_group(uint32_t* sm, const uint32_t* tws, u
     for (int j = 0; j < (1 << Q); j++) {
       uint32_t x = v[j];
       if (!INV && TWIST) x = fp_mul(x, tws[p0 + (j << G_LO)]);
+      if (PTW && INV) x = fp_mul(x, pt[j]);
       base[(j << G_LO) * PITCH_P] = x;
     }
   }
@@ -342,6 +395,54 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(PassArgs a) {
   }
 }
 
+
+// Strided pass with TMA staging (in place).  Same arithmetic as ntt_pass_kernel<INV, 1, R, false>.
+template <bool INV, int R>
+__global__ void __launch_bounds__(256) ntt_pass_tma_kernel(const __grid_constant__ CUtensorMap tmap, PassArgs a) {
+  constexpr int Q1 = R < 4 ? R : 4;
+  constexpr int Q2 = R - Q1;
+  constexpr unsigned NPTS = 1u << R;
+  constexpr unsigned TILE = NPTS * 32u;
+  extern __shared__ __align__(128) uint32_t sm[];
+  __shared__ __align__(8) uint64_t bar;
+  uint32_t* tws = sm + TILE;
+  const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const unsigned lo_blocks_log = a.s_lo - 5;
+  const unsigned hi = blockIdx.x >> lo_blocks_log;
+  const unsigned lo_blk = blockIdx.x & ((1u << lo_blocks_log) - 1);
+  if (tid == 0) mbar_init(&bar, 1);
+  if (Q2 > 0) {
+    for (unsigned p = tid; p < NPTS; p += blockDim.x) tws[p] = a.group_twist[p];
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar, TILE * 4);
+    tma_load_3d(sm, &tmap, &bar, (int)(lo_blk << 5), 0, (int)hi);
+  }
+  // inter-pass twist table index of (point p, this lane) = (tbase + p * 2^s_lo) & mask  (the block index hi drops out)
+  const uint32_t pmask = (uint32_t)((((size_t)1 << (a.s_lo + R)) - 1));
+  const uint32_t tbase = (lo_blk << 5) + lane;
+  const uint32_t pstride = 1u << a.s_lo;
+  mbar_wait(&bar, 0);
+  if (!INV) {
+    radix_group<R, Q1, 0, false, false, 1, (Q2 > 0), true>(sm, tws, lane, warp, nwarps, a.pass_twist, tbase, pstride, pmask);
+    if (Q2 > 0) {
+      __syncthreads();
+      radix_group<R, (Q2 > 0 ? Q2 : 1), Q1, false, false, 1, false>(sm, tws, lane, warp, nwarps);
+    }
+  } else {
+    if (Q2 > 0) {
+      radix_group<R, (Q2 > 0 ? Q2 : 1), Q1, false, true, 1, false>(sm, tws, lane, warp, nwarps);
+      __syncthreads();
+    }
+    radix_group<R, Q1, 0, false, true, 1, (Q2 > 0), true>(sm, tws, lane, warp, nwarps, a.pass_twist, tbase, pstride, pmask);
+  }
+  // make the generic-proxy writes visible to the async proxy, then one thread stores the tile
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (tid == 0) tma_store_3d(&tmap, sm, (int)(lo_blk << 5), 0, (int)hi);
+}
+
 // split logn into passes of <= 8 bits, first pass largest; every later pass needs s_lo >= 5 (32 adjacent lanes)
 static void plan_passes(unsigned logn, unsigned* R, unsigned* np) {
   unsigned n = (logn + 7) / 8;
@@ -381,9 +482,61 @@ static b2z_err launch_inst(b2z_ctx* ctx, const PassArgs& a) {
   B2Z_CUDA(cudaGetLastError());
   return nullptr;
 }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encoder() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+// B2Z_NTT_TMA=0 disables the TMA path (plain LDG/STG staging, same arithmetic)
+static bool tma_enabled() {
+  static bool on = [] {
+    const char* e = getenv("B2Z_NTT_TMA");
+    return !(e && e[0] == '0') && get_encoder() != nullptr;
+  }();
+  return on;
+}
+template <bool INV, int R>
+static b2z_err launch_tma(b2z_ctx* ctx, const PassArgs& a) {
+  constexpr unsigned NPTS = 1u << R;
+  const size_t tile_elems = (size_t)NPTS * 32;
+  B2Z_REQUIRE(a.total % tile_elems == 0 && a.in == a.out, "TMA NTT pass needs whole in-place tiles");
+  CUtensorMap tmap;
+  cuuint64_t dims[3] = {(cuuint64_t)1 << a.s_lo, NPTS, (cuuint64_t)(a.total >> (a.s_lo + R))};
+  cuuint64_t strides[2] = {(cuuint64_t)4 << a.s_lo, (cuuint64_t)4 << (a.s_lo + R)};
+  cuuint32_t box[3] = {32, NPTS, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult rc = get_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, a.out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B2Z_REQUIRE(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed");
+  size_t smem = sizeof(uint32_t) * (32 * NPTS + NPTS);
+  ntt_pass_tma_kernel<INV, R><<<(unsigned)(a.total / tile_elems), 256, smem, ctx->stream>>>(tmap, a);
+  ctx->launches++;
+  B2Z_CUDA(cudaGetLastError());
+  return nullptr;
+}
+
 template <bool INV, int FIRST>
 static b2z_err launch_one(b2z_ctx* ctx, const PassArgs& a, unsigned R) {
   const bool rows = (a.s_lo == 0);
+  // strided in-place passes with >= 128-byte aligned rows go through TMA
+  if (!rows && a.in == a.out && tma_enabled() && R >= 4 && (a.total >> (a.s_lo + R)) < (1ull << 31)) {
+    switch (R) {
+      case 4: return launch_tma<INV, 4>(ctx, a);
+      case 5: return launch_tma<INV, 5>(ctx, a);
+      case 6: return launch_tma<INV, 6>(ctx, a);
+      case 7: return launch_tma<INV, 7>(ctx, a);
+      case 8: return launch_tma<INV, 8>(ctx, a);
+      default: break;
+    }
+  }
 #define B2Z_NTT_CASE(RR)                                                         \
   case RR:                                                                       \
     return rows ? launch_inst<INV, FIRST, RR, true>(ctx, a) : launch_inst<INV, 1, RR, false>(ctx, a);
