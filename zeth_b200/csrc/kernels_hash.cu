@@ -26,8 +26,9 @@ static b2z_err upload_consts(b2z_ctx* ctx) {
   return nullptr;
 }
 
-__global__ void __launch_bounds__(128) hash_rows_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ matrix, size_t rows,
-                                                        size_t cols, uint32_t ones) {
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) hash_rows_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ matrix, size_t rows,
+                                                                  size_t cols, uint32_t ones) {
   size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (r >= rows) return;
   uint32_t s[P2_CELLS];
@@ -66,7 +67,15 @@ __global__ void __launch_bounds__(128) hash_fold_kernel(uint32_t* __restrict__ n
 b2z_err launch_hash_rows(b2z_ctx* ctx, uint32_t* out, const uint32_t* matrix, size_t rows, size_t cols) {
   if (rows == 0) return nullptr;
   B2Z_TRY(upload_consts(ctx));
-  hash_rows_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, ctx->stream>>>(out, matrix, rows, cols, 0xffffffffu);
+  // launch-shape experiments: B2Z_HASH_VARIANT = 0 (128 threads, compiler-chosen registers) | 1 (<= 48 regs) | 2 (<= 40 regs) | 3 (256 threads)
+  static int variant = [] { const char* e = getenv("B2Z_HASH_VARIANT"); return e ? atoi(e) : 0; }();
+  switch (variant) {
+    case 1: hash_rows_kernel<128, 10><<<(unsigned)((rows + 127) / 128), 128, 0, ctx->stream>>>(out, matrix, rows, cols, 0xffffffffu); break;
+    case 2: hash_rows_kernel<128, 12><<<(unsigned)((rows + 127) / 128), 128, 0, ctx->stream>>>(out, matrix, rows, cols, 0xffffffffu); break;
+    case 3: hash_rows_kernel<256, 4><<<(unsigned)((rows + 255) / 256), 256, 0, ctx->stream>>>(out, matrix, rows, cols, 0xffffffffu); break;
+    case 4: hash_rows_kernel<64, 16><<<(unsigned)((rows + 63) / 64), 64, 0, ctx->stream>>>(out, matrix, rows, cols, 0xffffffffu); break;
+    default: hash_rows_kernel<128, 1><<<(unsigned)((rows + 127) / 128), 128, 0, ctx->stream>>>(out, matrix, rows, cols, 0xffffffffu); break;
+  }
   ctx->launches++;
   B2Z_CUDA(cudaGetLastError());
   return nullptr;

@@ -197,7 +197,9 @@ __device__ __forceinline__ void radix_group(uint32_t* sm, const uint32_t* tws, u
   constexpr unsigned PITCH_L = ROWS ? ((1u << R) + 1u) : 1u;
   constexpr unsigned SETS = 1u << (R - Q);
   uint32_t* lane_base = sm + lane * PITCH_L;
-  for (unsigned set = warp; set < SETS; set += nwarps) {
+  (void)nwarps;  // kernels always run 8 warps; a compile-time stride lets the set loop unroll (no stack-resident v[])
+#pragma unroll
+  for (unsigned set = warp; set < SETS; set += 8) {
     // set index -> the point bits outside [G_LO, G_LO+Q)
     const unsigned low = set & ((1u << G_LO) - 1), high = set >> G_LO;
     const unsigned p0 = (high << (G_LO + Q)) | low;
