@@ -54,7 +54,8 @@ __global__ void ea_powers_kernel(uint32_t* __restrict__ pw, Fp4 x, size_t n) {
     cur = fp4_mul(cur, x);
   }
 }
-// group g: evaluations evs[g*EA_GROUP .. +EA_GROUP) (column ids in cols[], -1 padded), all at the point of table pw_of[g]
+// group g: evaluations evs[g*EA_GROUP .. +EA_GROUP) (column ids in cols[], -1 padded), all at the point of table pw_of[g].
+// A thread owns quads of 4 consecutive coefficients: one 128-bit load per column and four 128-bit loads of powers per quad.
 __global__ void __launch_bounds__(EA_THREADS) ea_dot_kernel(const uint32_t* __restrict__ coeffs, size_t n,
                                                             const int* __restrict__ cols, const uint32_t* const* __restrict__ pw_of,
                                                             uint32_t* __restrict__ partial, unsigned chunks) {
@@ -68,33 +69,59 @@ __global__ void __launch_bounds__(EA_THREADS) ea_dot_kernel(const uint32_t* __re
 #pragma unroll
   for (unsigned e = 0; e < EA_GROUP; e++) acc[e] = fp4_zero();
   const size_t base = (size_t)chunk * EA_THREADS * EA_PER_THREAD;
-#pragma unroll 2
-  for (unsigned k = 0; k < EA_PER_THREAD; k++) {
-    size_t j = base + t + (size_t)k * EA_THREADS;
-    if (j >= n) break;
-    uint4 pv = *reinterpret_cast<const uint4*>(pw + 4 * j);
+  if (n >= 4) {
+#pragma unroll 1
+    for (unsigned k = 0; k < EA_PER_THREAD / 4; k++) {
+      size_t j = base + 4 * ((size_t)t + (size_t)k * EA_THREADS);
+      if (j >= n) break;
+      uint4 p0 = *reinterpret_cast<const uint4*>(pw + 4 * j);
+      uint4 p1 = *reinterpret_cast<const uint4*>(pw + 4 * j + 4);
+      uint4 p2 = *reinterpret_cast<const uint4*>(pw + 4 * j + 8);
+      uint4 p3 = *reinterpret_cast<const uint4*>(pw + 4 * j + 12);
+      uint4 cv[EA_GROUP];
 #pragma unroll
-    for (unsigned e = 0; e < EA_GROUP; e++) {
-      if (col[e] < 0) continue;
-      uint32_t c = __ldg(coeffs + (size_t)col[e] * n + j);
-      acc[e].e[0] = fp_add(acc[e].e[0], fp_mul(pv.x, c));
-      acc[e].e[1] = fp_add(acc[e].e[1], fp_mul(pv.y, c));
-      acc[e].e[2] = fp_add(acc[e].e[2], fp_mul(pv.z, c));
-      acc[e].e[3] = fp_add(acc[e].e[3], fp_mul(pv.w, c));
+      for (unsigned e = 0; e < EA_GROUP; e++)
+        cv[e] = col[e] >= 0 ? __ldg(reinterpret_cast<const uint4*>(coeffs + (size_t)col[e] * n + j)) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (unsigned e = 0; e < EA_GROUP; e++) {
+        Fp4 a = acc[e];
+        a.e[0] = fp_add(a.e[0], fp_add(fp_add(fp_mul(p0.x, cv[e].x), fp_mul(p1.x, cv[e].y)), fp_add(fp_mul(p2.x, cv[e].z), fp_mul(p3.x, cv[e].w))));
+        a.e[1] = fp_add(a.e[1], fp_add(fp_add(fp_mul(p0.y, cv[e].x), fp_mul(p1.y, cv[e].y)), fp_add(fp_mul(p2.y, cv[e].z), fp_mul(p3.y, cv[e].w))));
+        a.e[2] = fp_add(a.e[2], fp_add(fp_add(fp_mul(p0.z, cv[e].x), fp_mul(p1.z, cv[e].y)), fp_add(fp_mul(p2.z, cv[e].z), fp_mul(p3.z, cv[e].w))));
+        a.e[3] = fp_add(a.e[3], fp_add(fp_add(fp_mul(p0.w, cv[e].x), fp_mul(p1.w, cv[e].y)), fp_add(fp_mul(p2.w, cv[e].z), fp_mul(p3.w, cv[e].w))));
+        acc[e] = a;
+      }
+    }
+  } else {  // tiny polynomials (n < 4): scalar path
+    for (size_t j = base + t; j < n && j < base + (size_t)EA_THREADS * EA_PER_THREAD; j += EA_THREADS) {
+      uint4 pv = *reinterpret_cast<const uint4*>(pw + 4 * j);
+      for (unsigned e = 0; e < EA_GROUP; e++) {
+        if (col[e] < 0) continue;
+        uint32_t c = __ldg(coeffs + (size_t)col[e] * n + j);
+        acc[e].e[0] = fp_add(acc[e].e[0], fp_mul(pv.x, c));
+        acc[e].e[1] = fp_add(acc[e].e[1], fp_mul(pv.y, c));
+        acc[e].e[2] = fp_add(acc[e].e[2], fp_mul(pv.z, c));
+        acc[e].e[3] = fp_add(acc[e].e[3], fp_mul(pv.w, c));
+      }
     }
   }
+  // block reduction: warp shuffles first, then one shared-memory step per evaluation
   for (unsigned e = 0; e < EA_GROUP; e++) {
-    red[t] = acc[e];
-    __syncthreads();
-    for (unsigned s = EA_THREADS / 2; s > 0; s >>= 1) {
-      if (t < s) red[t] = fp4_add(red[t], red[t + s]);
-      __syncthreads();
+    Fp4 v = acc[e];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      Fp4 o = fp4_make(__shfl_down_sync(0xffffffffu, v.e[0], off), __shfl_down_sync(0xffffffffu, v.e[1], off),
+                       __shfl_down_sync(0xffffffffu, v.e[2], off), __shfl_down_sync(0xffffffffu, v.e[3], off));
+      v = fp4_add(v, o);
     }
-    if (t == 0) {
-      uint32_t* o = partial + 4 * (((size_t)g * EA_GROUP + e) * chunks + chunk);
-      o[0] = red[0].e[0]; o[1] = red[0].e[1]; o[2] = red[0].e[2]; o[3] = red[0].e[3];
-    }
-    __syncthreads();
+    if ((t & 31) == 0) red[e * (EA_THREADS / 32) + (t >> 5)] = v;
+  }
+  __syncthreads();
+  if (t < EA_GROUP) {
+    Fp4 tot = fp4_zero();
+    for (unsigned w = 0; w < EA_THREADS / 32; w++) tot = fp4_add(tot, red[t * (EA_THREADS / 32) + w]);
+    uint32_t* o = partial + 4 * (((size_t)g * EA_GROUP + t) * chunks + chunk);
+    o[0] = tot.e[0]; o[1] = tot.e[1]; o[2] = tot.e[2]; o[3] = tot.e[3];
   }
 }
 // out[dst[s]] = sum over chunks of partial[s]
