@@ -219,6 +219,14 @@ __device__ __forceinline__ u32 ldc(const u32* col, u32 off) {
   asm volatile("{ .reg .u64 a; cvt.u64.u32 a, %2; add.u64 a, a, %1; ld.global.nc.u32 %0, [a]; }" : "=r"(v) : "l"(col), "r"(off));
   return v;
 }
+// asynchronous global -> shared copy of one word (LDGSTS): tap values are prefetched a whole phase ahead into per-thread
+// shared-memory slots, so deep memory-level parallelism costs no registers
+__device__ __forceinline__ void cpa(u32* sdst, const u32* col, u32 off) {
+  asm volatile("{ .reg .u64 a; .reg .u32 s; cvt.u64.u32 a, %2; add.u64 a, a, %1; cvt.u32.u64 s, %0; cp.async.ca.shared.global [s], [a], 4; }"
+               :: "l"(__cvta_generic_to_shared(sdst)), "l"(col), "r"(off) : "memory");
+}
+__device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cpa_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ E eld(const u32* p) {
   E r; asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.a), "=r"(r.b), "=r"(r.c), "=r"(r.d) : "l"(p)); return r;
 }
@@ -241,6 +249,7 @@ struct Val {
   Opd c[4];
   bool leaf_load = false;  // re-emit the load at each use
   std::string load_expr;
+  std::string load_col, load_off;  // column pointer / row offset expressions of a tap load (for staging)
 };
 struct Emitter {
   const b2z_circuit* c;
@@ -248,6 +257,31 @@ struct Emitter {
   std::ostringstream* o;
   std::vector<Val> vals;
   unsigned tmp = 0;
+  // staged tap loads (eval_check only): pass 1 records the ordered list of loads, pass 2 reads them from shared memory
+  int stage_k = 0;                                   // loads per phase, 0 = direct loads
+  bool recording = false;
+  std::vector<std::pair<std::string, std::string>>* load_list = nullptr;  // (column pointer expr, row offset expr)
+  unsigned load_idx = 0;
+  void phase_boundary(unsigned p) {
+    auto issue = [&](unsigned ph) {
+      for (unsigned L = ph * stage_k; L < (ph + 1) * (unsigned)stage_k && L < load_list->size(); L++)
+        *o << "  cpa(&stage[" << ((ph & 1) * stage_k + (L % stage_k)) << "][threadIdx.x], " << (*load_list)[L].first << ", " << (*load_list)[L].second << ");\n";
+      *o << "  cpa_commit();\n";
+    };
+    if (p == 0) issue(0);
+    issue(p + 1);
+    *o << "  cpa_wait1();\n";
+  }
+  Opd staged_load(const std::string& colp, const std::string& off) {
+    if (recording) {
+      load_list->push_back({colp, off});
+      return named("0u");
+    }
+    unsigned L = load_idx++;
+    if (L % stage_k == 0) phase_boundary(L / stage_k);
+    unsigned ph = L / stage_k;
+    return emit("stage[" + std::to_string((ph & 1) * stage_k + (L % stage_k)) + "][threadIdx.x]");
+  }
   static Opd konst(uint32_t k) { Opd r; r.is_const = true; r.k = k; return r; }
   static Opd named(const std::string& n) { Opd r; r.is_const = false; r.name = n; return r; }
   Opd emit(const std::string& expr) {
@@ -282,7 +316,8 @@ struct Emitter {
   Val use(size_t v) {
     Val r = vals[v];
     if (r.leaf_load) {
-      r.c[0] = emit(r.load_expr);
+      if (stage_k > 0 && !r.load_col.empty()) r.c[0] = staged_load(r.load_col, r.load_off);
+      else r.c[0] = emit(r.load_expr);
       r.leaf_load = false;
     }
     return r;
@@ -340,7 +375,9 @@ struct Emitter {
         uint32_t g = c->tap_group[s.a], col = c->tap_offset[s.a], back = c->tap_back[s.a];
         r.ext = false;
         r.leaf_load = true;
-        r.load_expr = "ldc(cp.g" + std::to_string(g) + "[" + std::to_string(col) + "], ib" + std::to_string(back) + ")";
+        r.load_col = "cp.g" + std::to_string(g) + "[" + std::to_string(col) + "]";
+        r.load_off = "ib" + std::to_string(back);
+        r.load_expr = "ldc(" + r.load_col + ", " + r.load_off + ")";
       } break;
       case OP_GET_GLOBAL:
         if (trace_domain) {
@@ -396,31 +433,46 @@ void circuit_codegen(b2z_circuit* c) {
   o << "  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;\n  if (i > mask) return;\n  const u64 domain = mask + 1;\n";
   for (unsigned b = 0; b <= max_back; b++) o << "  const u32 ib" << b << " = (u32)((i - " << 4 * b << "ull) & mask) << 2;\n";
   {
-    Emitter em{c, false, &o, {}, 0};
-    std::vector<Val> mixv;  // accumulated `tot` of every mix variable
-    for (const auto& s : c->steps) {
-      switch (s.op) {
-        case OP_TRUE: {
-          Val z;
-          z.ext = true;
-          mixv.push_back(z);  // all four components constant 0
-        } break;
-        case OP_AND_EQZ: {
-          Val term = em.v_mul(pw_val(c->mix_exp[s.a]), em.use(s.b));
-          mixv.push_back(em.v_add(mixv[s.a], term, false));
-        } break;
-        case OP_AND_COND: {
-          Val inner = em.v_mul(mixv[s.c], em.use(s.b));
-          Val term = em.v_mul(inner, pw_val(c->mix_exp[s.a]));
-          mixv.push_back(em.v_add(mixv[s.a], term, false));
-        } break;
-        default: em.step(s); break;
+    // B2Z_EVALCHECK_STAGE = K > 0: prefetch tap values K loads (one phase) ahead through shared memory with cp.async
+    int stage_k = 24;
+    if (const char* e = getenv("B2Z_EVALCHECK_STAGE")) stage_k = atoi(e);
+    std::vector<std::pair<std::string, std::string>> load_list;
+    auto run = [&](std::ostringstream& out, bool recording) {
+      Emitter em{c, false, &out, {}, 0};
+      em.stage_k = stage_k;
+      em.recording = recording;
+      em.load_list = &load_list;
+      std::vector<Val> mixv;  // accumulated `tot` of every mix variable
+      for (const auto& s : c->steps) {
+        switch (s.op) {
+          case OP_TRUE: {
+            Val z;
+            z.ext = true;
+            mixv.push_back(z);  // all four components constant 0
+          } break;
+          case OP_AND_EQZ: {
+            Val term = em.v_mul(pw_val(c->mix_exp[s.a]), em.use(s.b));
+            mixv.push_back(em.v_add(mixv[s.a], term, false));
+          } break;
+          case OP_AND_COND: {
+            Val inner = em.v_mul(mixv[s.c], em.use(s.b));
+            Val term = em.v_mul(inner, pw_val(c->mix_exp[s.a]));
+            mixv.push_back(em.v_add(mixv[s.a], term, false));
+          } break;
+          default: em.step(s); break;
+        }
       }
+      out << "  const u32 iz = (i & 2) ? ((i & 1) ? iz3 : iz2) : ((i & 1) ? iz1 : iz0);\n";
+      Val r = em.v_mul(mixv[c->ret], Emitter::base(Emitter::named("iz")));
+      for (int k = 0; k < 4; k++) out << "  check[" << k << " * domain + i] = " << (r.ext || k == 0 ? r.c[k].str() : std::string("0u")) << ";\n";
+      out << "}\n\n";
+    };
+    if (stage_k > 0) {
+      std::ostringstream dry;
+      run(dry, true);  // pass 1: collect the ordered tap loads
+      o << "  __shared__ u32 stage[" << 2 * stage_k << "][128];\n";
     }
-    o << "  const u32 iz = (i & 2) ? ((i & 1) ? iz3 : iz2) : ((i & 1) ? iz1 : iz0);\n";
-    Val r = em.v_mul(mixv[c->ret], Emitter::base(Emitter::named("iz")));
-    for (int k = 0; k < 4; k++) o << "  check[" << k << " * domain + i] = " << (r.ext || k == 0 ? r.c[k].str() : std::string("0u")) << ";\n";
-    o << "}\n\n";
+    run(o, false);
   }
   // ---- witgen: one thread per active trace row; taps read the trace domain (stride 1) ----
   o << "extern \"C\" __global__ void __launch_bounds__(256) b2z_witgen(const __grid_constant__ ColPtrs cp, "

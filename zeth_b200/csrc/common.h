@@ -67,6 +67,8 @@ b2z_err launch_bit_reverse(b2z_ctx* ctx, uint32_t* io, size_t count, unsigned po
 b2z_err launch_zk_shift(b2z_ctx* ctx, uint32_t* io, size_t count, unsigned po2);
 b2z_err launch_hash_rows(b2z_ctx* ctx, uint32_t* out, const uint32_t* matrix, size_t rows, size_t cols);
 b2z_err launch_hash_fold(b2z_ctx* ctx, uint32_t* nodes, size_t in_size, size_t out_size);
+// all fold layers with <= start_out parents, one launch (node layout as hash_fold: in_size = 2 * out_size)
+b2z_err launch_hash_fold_top(b2z_ctx* ctx, uint32_t* nodes, size_t start_out);
 b2z_err launch_fri_fold(b2z_ctx* ctx, uint32_t* out, const uint32_t* in, const Fp4& mix, size_t out_count);
 b2z_err launch_evaluate_any(b2z_ctx* ctx, const uint32_t* coeffs, unsigned po2, const uint32_t* which, const uint32_t* xs,
                             size_t eval_count, uint32_t* out);

@@ -64,6 +64,32 @@ __global__ void __launch_bounds__(128) hash_fold_kernel(uint32_t* __restrict__ n
   o[1] = make_uint4(s[4], s[5], s[6], s[7]);
 }
 
+// Top of the tree in one launch: all layers from `start_out` parents down to the root are folded by a single CTA
+// (layer after layer, __syncthreads between them) -- replaces ~10 tiny launches per Merkle tree.
+constexpr unsigned FOLD_TOP_THREADS = 512;
+__global__ void __launch_bounds__(FOLD_TOP_THREADS) hash_fold_top_kernel(uint32_t* __restrict__ nodes, unsigned start_out, uint32_t ones) {
+  for (unsigned out_size = start_out; out_size >= 1; out_size >>= 1) {
+    for (unsigned j = threadIdx.x; j < out_size; j += blockDim.x) {
+      const uint4* in = reinterpret_cast<const uint4*>(nodes + 8 * (size_t)(2 * out_size + 2 * j));
+      uint4 a = in[0], b = in[1], c = in[2], d = in[3];
+      uint32_t s[P2_CELLS] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w, 0, 0, 0, 0, 0, 0, 0, 0};
+      p2_permute_dev(s, c_p2, ones);
+      uint4* o = reinterpret_cast<uint4*>(nodes + 8 * (size_t)(out_size + j));
+      o[0] = make_uint4(s[0], s[1], s[2], s[3]);
+      o[1] = make_uint4(s[4], s[5], s[6], s[7]);
+    }
+    __syncthreads();
+  }
+}
+b2z_err launch_hash_fold_top(b2z_ctx* ctx, uint32_t* nodes, size_t start_out) {
+  if (start_out == 0) return nullptr;
+  B2Z_TRY(upload_consts(ctx));
+  hash_fold_top_kernel<<<1, FOLD_TOP_THREADS, 0, ctx->stream>>>(nodes, (unsigned)start_out, 0xffffffffu);
+  ctx->launches++;
+  B2Z_CUDA(cudaGetLastError());
+  return nullptr;
+}
+
 b2z_err launch_hash_rows(b2z_ctx* ctx, uint32_t* out, const uint32_t* matrix, size_t rows, size_t cols) {
   if (rows == 0) return nullptr;
   B2Z_TRY(upload_consts(ctx));

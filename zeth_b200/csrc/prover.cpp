@@ -83,7 +83,17 @@ struct MerkleParams {
 
 b2z_err merkle_build(b2z_ctx* ctx, uint32_t* nodes, const uint32_t* matrix, size_t rows, size_t cols) {
   B2Z_TRY(launch_hash_rows(ctx, nodes + 8 * rows, matrix, rows, cols));
-  for (size_t i = ilog2(rows); i-- > 0;) B2Z_TRY(launch_hash_fold(ctx, nodes, (size_t)2 << i, (size_t)1 << i));
+  // wide layers: one launch each; the top of the tree (<= 512 parents per layer) in a single launch
+  constexpr size_t TOP = 512;
+  size_t i = ilog2(rows);
+  while (i-- > 0) {
+    size_t out = (size_t)1 << i;
+    if (out <= TOP) {
+      B2Z_TRY(launch_hash_fold_top(ctx, nodes, out));
+      break;
+    }
+    B2Z_TRY(launch_hash_fold(ctx, nodes, 2 * out, out));
+  }
   return nullptr;
 }
 
