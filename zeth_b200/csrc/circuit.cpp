@@ -433,8 +433,9 @@ void circuit_codegen(b2z_circuit* c) {
   o << "  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;\n  if (i > mask) return;\n  const u64 domain = mask + 1;\n";
   for (unsigned b = 0; b <= max_back; b++) o << "  const u32 ib" << b << " = (u32)((i - " << 4 * b << "ull) & mask) << 2;\n";
   {
-    // B2Z_EVALCHECK_STAGE = K > 0: prefetch tap values K loads (one phase) ahead through shared memory with cp.async
-    int stage_k = 24;
+    // B2Z_EVALCHECK_STAGE = K > 0: prefetch tap values K loads (one phase) ahead through shared memory with cp.async.
+    // Off by default: measured on B200 (planning circuit, po2 20) 3.78 ms direct vs 3.69-3.97 ms staged -- no gain.
+    int stage_k = 0;
     if (const char* e = getenv("B2Z_EVALCHECK_STAGE")) stage_k = atoi(e);
     std::vector<std::pair<std::string, std::string>> load_list;
     auto run = [&](std::ostringstream& out, bool recording) {
