@@ -57,11 +57,8 @@ b2z_err b2z_destroy(b2z_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   ntt_release_tables(ctx);
-  for (int i = 0; i <= MAX_PO2; i++) {
-    if (ctx->tw_fwd[i]) cudaFree(ctx->tw_fwd[i]);
-    if (ctx->tw_rev[i]) cudaFree(ctx->tw_rev[i]);
+  for (int i = 0; i <= MAX_PO2; i++)
     if (ctx->pow3rev[i]) cudaFree(ctx->pow3rev[i]);
-  }
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   for (auto& pr : ctx->phase_events) {
     cudaEventDestroy(pr.first);

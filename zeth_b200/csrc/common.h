@@ -44,9 +44,7 @@ struct b2z_ctx {
   cudaStream_t copy_stream = nullptr;          // host->device witness uploads overlapped with compute (b2z_prove_segment)
   std::vector<cudaEvent_t> h2d_events;
   uint64_t launches = 0;
-  // per-size device tables, built lazily: forward / inverse twiddles w_n^k (k < n/2), 3^rev(j) for zk_shift
-  uint32_t* tw_fwd[b2z::MAX_PO2 + 1] = {};
-  uint32_t* tw_rev[b2z::MAX_PO2 + 1] = {};
+  // per-size device table, built lazily: 3^rev(j) for zk_shift (NTT twist tables live in kernels_ntt.cu's registry)
   uint32_t* pow3rev[b2z::MAX_PO2 + 1] = {};
   // pinned staging for small transcript round trips
   uint32_t* pinned = nullptr;
@@ -59,7 +57,7 @@ struct b2z_ctx {
 namespace b2z {
 
 // ---- kernel launchers (kernels_*.cu); all enqueue on ctx->stream and bump ctx->launches ----
-b2z_err ensure_tables(b2z_ctx* ctx, unsigned po2, bool fwd, bool rev, bool pow3);
+b2z_err ensure_tables(b2z_ctx* ctx, unsigned po2, bool pow3);
 // `src` (optional): read the natural-order evaluations from a separate buffer (saves the witness -> coefficient copy)
 b2z_err launch_interpolate(b2z_ctx* ctx, uint32_t* io, size_t count, unsigned po2, bool fuse_zk_shift, const uint32_t* src = nullptr);
 b2z_err launch_evaluate(b2z_ctx* ctx, uint32_t* out, const uint32_t* in, size_t count, unsigned out_po2, unsigned expand_bits);
@@ -91,8 +89,7 @@ struct GatherTree {
   const uint32_t* matrix;
   const uint32_t* nodes;
   uint32_t rows, cols, top_size;
-  uint32_t seal_off;  // word offset of this tree's section inside one query record
-  uint32_t shift;     // query position -> row: idx = pos & (rows-1) for FRI rounds (pos % rows)
+  uint32_t seal_off;  // word offset of this tree's section inside one query record; row = pos & (rows - 1)
 };
 b2z_err launch_gather_queries(b2z_ctx* ctx, uint32_t* seal_dev, const GatherTree* trees_dev, size_t n_trees,
                               const uint32_t* positions_dev, size_t n_queries, size_t record_words);

@@ -79,7 +79,7 @@ void ntt_release_tables(b2z_ctx* ctx) {
   g_tables.erase(it);
 }
 
-b2z_err ensure_tables(b2z_ctx* ctx, unsigned po2, bool, bool, bool pow3) {
+b2z_err ensure_tables(b2z_ctx* ctx, unsigned po2, bool pow3) {
   B2Z_REQUIRE(po2 <= MAX_PO2, "transform size exceeds 2^26");
   static std::mutex w16_mutex;
   std::lock_guard<std::mutex> w16_lock(w16_mutex);
@@ -552,7 +552,7 @@ static b2z_err launch_one(b2z_ctx* ctx, const PassArgs& a, unsigned R) {
 // forward transform of `count` columns: out (2^logn per column) from in (2^(logn - ebits) per column when expanding)
 b2z_err launch_evaluate(b2z_ctx* ctx, uint32_t* out, const uint32_t* in, size_t count, unsigned out_po2, unsigned expand_bits) {
   if (count == 0) return nullptr;
-  B2Z_TRY(ensure_tables(ctx, out_po2, false, false, false));
+  B2Z_TRY(ensure_tables(ctx, out_po2, false));
   const unsigned logn = out_po2;
   bool expanding = (in != out);
   if (logn == 0) {
@@ -605,7 +605,7 @@ b2z_err launch_evaluate(b2z_ctx* ctx, uint32_t* out, const uint32_t* in, size_t 
 b2z_err launch_interpolate(b2z_ctx* ctx, uint32_t* io, size_t count, unsigned po2, bool fuse_zk_shift, const uint32_t* src) {
   if (count == 0) return nullptr;
   if (src == io) src = nullptr;
-  B2Z_TRY(ensure_tables(ctx, po2, false, false, fuse_zk_shift));
+  B2Z_TRY(ensure_tables(ctx, po2, fuse_zk_shift));
   const unsigned logn = po2;
   if (logn == 0) {
     if (src) B2Z_CUDA(cudaMemcpyAsync(io, src, 4 * count, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -708,7 +708,7 @@ __global__ void zk_shift_kernel(uint32_t* io, const uint32_t* __restrict__ tab, 
 b2z_err launch_zk_shift(b2z_ctx* ctx, uint32_t* io, size_t count, unsigned po2) {
   size_t total = count << po2;
   if (!total) return nullptr;
-  B2Z_TRY(ensure_tables(ctx, po2, false, false, true));
+  B2Z_TRY(ensure_tables(ctx, po2, true));
   zk_shift_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(io, ctx->pow3rev[po2], po2, total);
   ctx->launches++;
   B2Z_CUDA(cudaGetLastError());

@@ -453,7 +453,7 @@ b2z_err prove_segment_device(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, c
     size_t off = 0;
     auto add_tree = [&](const uint32_t* matrix, const uint32_t* nodes, size_t rows, size_t cols) {
       MerkleParams mp(rows, cols);
-      GatherTree t{matrix, nodes, (uint32_t)rows, (uint32_t)cols, (uint32_t)mp.top_size, (uint32_t)off, 0};
+      GatherTree t{matrix, nodes, (uint32_t)rows, (uint32_t)cols, (uint32_t)mp.top_size, (uint32_t)off};
       trees.push_back(t);
       off += cols + mp.path_words();
     };
