@@ -126,7 +126,7 @@ def cpu_reference_run(steps: int, warmup: int, target_s: float = 12.0):
 
     one(12, 1)  # warm the thread pool / page in
     # samples smaller than po2 = 16 are dominated by fixed per-phase overheads on many-core hosts and under-report the CPU
-    probe_po2 = 16
+    probe_po2 = int(os.environ.get("B2Z_REF_MIN_PO2", "16"))  # (tests shrink it)
     est = min(one(probe_po2, 2), one(probe_po2, 3))
     total_runs = max(1, steps + warmup)
     per_run = max(target_s / total_runs, 0.5)
@@ -147,7 +147,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    value, cores, sample, ms, po2 = cpu_reference_run(args.steps, args.warmup, target_s=45.0)
+    value, cores, sample, ms, po2 = cpu_reference_run(args.steps, args.warmup, target_s=float(os.environ.get("B2Z_REF_TARGET_S", "45")))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
