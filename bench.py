@@ -369,7 +369,7 @@ def run_b2z(args):
         kernels.append({"kernel": "batch_interpolate_ntt (2 passes)", "ms": ms_in, "algorithmic_bytes": bytes_in,
                         "achieved_gbs": bytes_in / ms_in / 1e6, "frac_hbm": bytes_in / ms_in / 1e6 / hbm})
         del lde, dig, tmp
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # reported at N = 1 only
             v, cores, sample, _, _ = cpu_reference_run(1, 0, target_s=12.0)
             cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
 
