@@ -8,6 +8,9 @@
 //   * zk_shift is fused into the last iNTT pass; DEEP synthetic division runs on the GPU as a scan;
 //   * all 50 query openings (rows + Merkle paths of every tree) are produced by ONE gather kernel, because the
 //     query positions depend only on the transcript state, not on the opened data.
+#include <nvtx3/nvToolsExt.h>  // header-only; ranges show up in Nsight tools, no-ops otherwise
+
+#include <cstdlib>
 #include <cstring>
 
 #include "circuit.h"
@@ -31,8 +34,14 @@ struct PhaseTimer {
       }
     }
   }
-  void begin(size_t i) { cudaEventRecord(ctx->phase_events[i].first, ctx->stream); }
-  void end(size_t i) { cudaEventRecord(ctx->phase_events[i].second, ctx->stream); }
+  void begin(size_t i) {
+    nvtxRangePushA(PHASE_NAMES[i]);
+    cudaEventRecord(ctx->phase_events[i].first, ctx->stream);
+  }
+  void end(size_t i) {
+    cudaEventRecord(ctx->phase_events[i].second, ctx->stream);
+    nvtxRangePop();
+  }
   void collect() {
     ctx->phase_ms.assign(N_PHASES, 0.0);
     for (size_t i = 0; i < N_PHASES; i++) {
@@ -477,6 +486,14 @@ b2z_err prove_segment_device(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, c
   tm.end(10);
   B2Z_CUDA(cudaStreamSynchronize(ctx->stream));
   tm.collect();
+  if (const char* tr = getenv("B2Z_TRACE")) {
+    // one JSON line per segment on stderr (field names follow the reference harness: run-parallel.sh:15 `total_cycles`)
+    if (tr[0] != '0') {
+      fprintf(stderr, "{\"event\":\"segment_proved\",\"po2\":%u,\"total_cycles\":%zu,\"seal_words\":%zu", po2, n, seal_words);
+      for (size_t i = 0; i < N_PHASES; i++) fprintf(stderr, ",\"%s_ms\":%.3f", PHASE_NAMES[i], ctx->phase_ms[i]);
+      fprintf(stderr, "}\n");
+    }
+  }
   memcpy(seal_host, seal.w, 4 * seal_words);
   if (seal_words_out) *seal_words_out = seal_words;
   return nullptr;
