@@ -219,14 +219,6 @@ __device__ __forceinline__ u32 ldc(const u32* col, u32 off) {
   asm volatile("{ .reg .u64 a; cvt.u64.u32 a, %2; add.u64 a, a, %1; ld.global.nc.u32 %0, [a]; }" : "=r"(v) : "l"(col), "r"(off));
   return v;
 }
-// asynchronous global -> shared copy of one word (LDGSTS): tap values are prefetched a whole phase ahead into per-thread
-// shared-memory slots, so deep memory-level parallelism costs no registers
-__device__ __forceinline__ void cpa(u32* sdst, const u32* col, u32 off) {
-  asm volatile("{ .reg .u64 a; .reg .u32 s; cvt.u64.u32 a, %2; add.u64 a, a, %1; cvt.u32.u64 s, %0; cp.async.ca.shared.global [s], [a], 4; }"
-               :: "l"(__cvta_generic_to_shared(sdst)), "l"(col), "r"(off) : "memory");
-}
-__device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cpa_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ E eld(const u32* p) {
   E r; asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.a), "=r"(r.b), "=r"(r.c), "=r"(r.d) : "l"(p)); return r;
 }
@@ -241,6 +233,7 @@ __device__ __forceinline__ E eld(const u32* p) {
 struct Opd {
   bool is_const = true;
   uint32_t k = 0;     // Montgomery constant when is_const
+  int tid = -1;       // id of the temporary when the operand is one (statement collection / partitioning)
   std::string name;   // expression otherwise
   std::string str() const { return is_const ? std::to_string(k) + "u" : name; }
 };
@@ -257,37 +250,31 @@ struct Emitter {
   std::ostringstream* o;
   std::vector<Val> vals;
   unsigned tmp = 0;
-  // staged tap loads (eval_check only): pass 1 records the ordered list of loads, pass 2 reads them from shared memory
-  int stage_k = 0;                                   // loads per phase, 0 = direct loads
-  bool recording = false;
-  std::vector<std::pair<std::string, std::string>>* load_list = nullptr;  // (column pointer expr, row offset expr)
-  unsigned load_idx = 0;
-  void phase_boundary(unsigned p) {
-    auto issue = [&](unsigned ph) {
-      for (unsigned L = ph * stage_k; L < (ph + 1) * (unsigned)stage_k && L < load_list->size(); L++)
-        *o << "  cpa(&stage[" << ((ph & 1) * stage_k + (L % stage_k)) << "][threadIdx.x], " << (*load_list)[L].first << ", " << (*load_list)[L].second << ");\n";
-      *o << "  cpa_commit();\n";
-    };
-    if (p == 0) issue(0);
-    issue(p + 1);
-    *o << "  cpa_wait1();\n";
-  }
-  Opd staged_load(const std::string& colp, const std::string& off) {
-    if (recording) {
-      load_list->push_back({colp, off});
-      return named("0u");
-    }
-    unsigned L = load_idx++;
-    if (L % stage_k == 0) phase_boundary(L / stage_k);
-    unsigned ph = L / stage_k;
-    return emit("stage[" + std::to_string((ph & 1) * stage_k + (L % stage_k)) + "][threadIdx.x]");
-  }
   static Opd konst(uint32_t k) { Opd r; r.is_const = true; r.k = k; return r; }
   static Opd named(const std::string& n) { Opd r; r.is_const = false; r.name = n; return r; }
-  Opd emit(const std::string& expr) {
-    std::string n = "t" + std::to_string(tmp++);
-    *o << "  const u32 " << n << " = " << expr << ";\n";
-    return named(n);
+  // collect mode: statements are recorded (with the temporaries they read) instead of printed, so that the program can
+  // be cut into __noinline__ parts afterwards
+  struct Stmt {
+    unsigned id;
+    std::string expr;
+    std::vector<unsigned> uses;
+  };
+  std::vector<Stmt>* stmts = nullptr;
+  std::string cp_name = "cp", kc_name = "kc";
+  Opd emit(const std::string& expr, const Opd* a = nullptr, const Opd* b = nullptr) {
+    unsigned id = tmp++;
+    std::string n = "t" + std::to_string(id);
+    if (stmts) {
+      Stmt st{id, expr, {}};
+      if (a && a->tid >= 0) st.uses.push_back((unsigned)a->tid);
+      if (b && b->tid >= 0) st.uses.push_back((unsigned)b->tid);
+      stmts->push_back(st);
+    } else {
+      *o << "  const u32 " << n << " = " << expr << ";\n";
+    }
+    Opd r = named(n);
+    r.tid = (int)id;
+    return r;
   }
   Opd s_mul(const Opd& a, const Opd& b) {
     if (a.is_const && b.is_const) return konst(fp_mul(a.k, b.k));
@@ -299,25 +286,24 @@ struct Emitter {
       if (b.k == 0) return konst(0);
       if (b.k == MONT_ONE) return a;
     }
-    return emit("fmul(" + a.str() + ", " + b.str() + ")");
+    return emit("fmul(" + a.str() + ", " + b.str() + ")", &a, &b);
   }
   Opd s_add(const Opd& a, const Opd& b) {
     if (a.is_const && b.is_const) return konst(fp_add(a.k, b.k));
     if (a.is_const && a.k == 0) return b;
     if (b.is_const && b.k == 0) return a;
-    return emit("fadd(" + a.str() + ", " + b.str() + ")");
+    return emit("fadd(" + a.str() + ", " + b.str() + ")", &a, &b);
   }
   Opd s_sub(const Opd& a, const Opd& b) {
     if (a.is_const && b.is_const) return konst(fp_sub(a.k, b.k));
     if (b.is_const && b.k == 0) return a;
-    return emit("fsub(" + a.str() + ", " + b.str() + ")");
+    return emit("fsub(" + a.str() + ", " + b.str() + ")", &a, &b);
   }
   // operand view of a value; leaves are loaded here (fresh temporary per use)
   Val use(size_t v) {
     Val r = vals[v];
     if (r.leaf_load) {
-      if (stage_k > 0 && !r.load_col.empty()) r.c[0] = staged_load(r.load_col, r.load_off);
-      else r.c[0] = emit(r.load_expr);
+      r.c[0] = emit(r.load_expr);
       r.leaf_load = false;
     }
     return r;
@@ -375,7 +361,7 @@ struct Emitter {
         uint32_t g = c->tap_group[s.a], col = c->tap_offset[s.a], back = c->tap_back[s.a];
         r.ext = false;
         r.leaf_load = true;
-        r.load_col = "cp.g" + std::to_string(g) + "[" + std::to_string(col) + "]";
+        r.load_col = cp_name + ".g" + std::to_string(g) + "[" + std::to_string(col) + "]";
         r.load_off = "ib" + std::to_string(back);
         r.load_expr = "ldc(" + r.load_col + ", " + r.load_off + ")";
       } break;
@@ -385,7 +371,7 @@ struct Emitter {
           r.leaf_load = true;
           r.load_expr = "ldv(globals + " + std::to_string(s.b) + ")";
         } else {
-          r = base(named(std::string(s.a == 0 ? "kc.g[" : "kc.m[") + std::to_string(s.b) + "]"));
+          r = base(named(kc_name + (s.a == 0 ? ".g[" : ".m[") + std::to_string(s.b) + "]"));
         }
         break;
       case OP_ADD: r = v_add(use(s.a), use(s.b), false); break;
@@ -397,14 +383,14 @@ struct Emitter {
   }
 };
 
-static Val pw_val(uint32_t e) {
+static Val pw_val(uint32_t e, const std::string& kc_name = "kc") {
   Val r;
   r.ext = true;
   if (e == 0) {
     r.c[0] = Emitter::konst(MONT_ONE);
     for (int i = 1; i < 4; i++) r.c[i] = Emitter::konst(0);
   } else {
-    for (int i = 0; i < 4; i++) r.c[i] = Emitter::named("kc.pw[" + std::to_string(4 * e + i) + "]");
+    for (int i = 0; i < 4; i++) r.c[i] = Emitter::named(kc_name + ".pw[" + std::to_string(4 * e + i) + "]");
   }
   return r;
 }
@@ -428,52 +414,116 @@ void circuit_codegen(b2z_circuit* c) {
   // they are instruction operands and cost neither loads nor registers
   o << "struct Consts { u32 g[" << (c->globals_size ? c->globals_size : 1) << "]; u32 m[" << (c->mix_size ? c->mix_size : 1)
     << "]; u32 pw[" << 4 * (c->max_exp + 1) << "]; };\n";
-  o << "extern \"C\" __global__ void __launch_bounds__(128, " << min_blocks << ") b2z_eval_check(u32* __restrict__ check, const __grid_constant__ ColPtrs cp, "
-       "const __grid_constant__ Consts kc, u32 iz0, u32 iz1, u32 iz2, u32 iz3, u64 mask) {\n";
-  o << "  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;\n  if (i > mask) return;\n  const u64 domain = mask + 1;\n";
-  for (unsigned b = 0; b <= max_back; b++) o << "  const u32 ib" << b << " = (u32)((i - " << 4 * b << "ull) & mask) << 2;\n";
+  // B2Z_EVALCHECK_PARTS = M > 0: cut the straight-line program into __noinline__ device functions of about M statements
+  // (cuts right after a constraint has been accumulated, so only the accumulator and the few shared temporaries cross a
+  // cut).  The generated CUDA of upstream's rv32im circuit is split the same way; ptxas cannot hoist loads across calls,
+  // which is what makes one huge basic block spill.  Tables then live in module-level __constant__ memory.
+  int parts_m = 0;
+  if (const char* e = getenv("B2Z_EVALCHECK_PARTS")) parts_m = atoi(e);
+  c->parts_mode = parts_m > 0;
+  const std::string cpn = parts_m > 0 ? "ccp" : "cp", kcn = parts_m > 0 ? "ckc" : "kc";
+  std::ostringstream body;  // straight-line mode: kernel body text
+  std::vector<Emitter::Stmt> stmts;
+  std::vector<size_t> cut_points;  // statement counts at which a cut is allowed
+  Val result;
   {
-    // B2Z_EVALCHECK_STAGE = K > 0: prefetch tap values K loads (one phase) ahead through shared memory with cp.async.
-    // Off by default: measured on B200 (planning circuit, po2 20) 3.78 ms direct vs 3.69-3.97 ms staged -- no gain.
-    int stage_k = 0;
-    if (const char* e = getenv("B2Z_EVALCHECK_STAGE")) stage_k = atoi(e);
-    std::vector<std::pair<std::string, std::string>> load_list;
-    auto run = [&](std::ostringstream& out, bool recording) {
-      Emitter em{c, false, &out, {}, 0};
-      em.stage_k = stage_k;
-      em.recording = recording;
-      em.load_list = &load_list;
-      std::vector<Val> mixv;  // accumulated `tot` of every mix variable
-      for (const auto& s : c->steps) {
-        switch (s.op) {
-          case OP_TRUE: {
-            Val z;
-            z.ext = true;
-            mixv.push_back(z);  // all four components constant 0
-          } break;
-          case OP_AND_EQZ: {
-            Val term = em.v_mul(pw_val(c->mix_exp[s.a]), em.use(s.b));
-            mixv.push_back(em.v_add(mixv[s.a], term, false));
-          } break;
-          case OP_AND_COND: {
-            Val inner = em.v_mul(mixv[s.c], em.use(s.b));
-            Val term = em.v_mul(inner, pw_val(c->mix_exp[s.a]));
-            mixv.push_back(em.v_add(mixv[s.a], term, false));
-          } break;
-          default: em.step(s); break;
-        }
+    Emitter em{c, false, &body, {}, 0};
+    em.cp_name = cpn;
+    em.kc_name = kcn;
+    if (parts_m > 0) em.stmts = &stmts;
+    std::vector<Val> mixv;  // accumulated `tot` of every mix variable
+    for (const auto& s : c->steps) {
+      switch (s.op) {
+        case OP_TRUE: {
+          Val z;
+          z.ext = true;
+          mixv.push_back(z);  // all four components constant 0
+        } break;
+        case OP_AND_EQZ: {
+          Val term = em.v_mul(pw_val(c->mix_exp[s.a], kcn), em.use(s.b));
+          mixv.push_back(em.v_add(mixv[s.a], term, false));
+          cut_points.push_back(stmts.size());
+        } break;
+        case OP_AND_COND: {
+          Val inner = em.v_mul(mixv[s.c], em.use(s.b));
+          Val term = em.v_mul(inner, pw_val(c->mix_exp[s.a], kcn));
+          mixv.push_back(em.v_add(mixv[s.a], term, false));
+          cut_points.push_back(stmts.size());
+        } break;
+        default: em.step(s); break;
       }
-      out << "  const u32 iz = (i & 2) ? ((i & 1) ? iz3 : iz2) : ((i & 1) ? iz1 : iz0);\n";
-      Val r = em.v_mul(mixv[c->ret], Emitter::base(Emitter::named("iz")));
-      for (int k = 0; k < 4; k++) out << "  check[" << k << " * domain + i] = " << (r.ext || k == 0 ? r.c[k].str() : std::string("0u")) << ";\n";
-      out << "}\n\n";
-    };
-    if (stage_k > 0) {
-      std::ostringstream dry;
-      run(dry, true);  // pass 1: collect the ordered tap loads
-      o << "  __shared__ u32 stage[" << 2 * stage_k << "][128];\n";
     }
-    run(o, false);
+    result = mixv[c->ret];
+  }
+  const std::string kernel_head_params = "u32* __restrict__ check, const __grid_constant__ ColPtrs cp, const __grid_constant__ Consts kc, "
+                                         "u32 iz0, u32 iz1, u32 iz2, u32 iz3, u64 mask";
+  auto emit_tail = [&](std::ostringstream& out) {
+    out << "  const u32 iz = (i & 2) ? ((i & 1) ? iz3 : iz2) : ((i & 1) ? iz1 : iz0);\n";
+    for (int k = 0; k < 4; k++) {
+      std::string v = (result.ext || k == 0) ? result.c[k].str() : std::string("0u");
+      out << "  check[" << k << " * domain + i] = fmul(" << v << ", iz);\n";
+    }
+    out << "}\n\n";
+  };
+  std::string ib_args, ib_params;
+  for (unsigned b = 0; b <= max_back; b++) {
+    ib_args += (b ? ", ib" : "ib") + std::to_string(b);
+    ib_params += (b ? ", u32 ib" : "u32 ib") + std::to_string(b);
+  }
+  if (parts_m <= 0) {
+    o << "extern \"C\" __global__ void __launch_bounds__(128, " << min_blocks << ") b2z_eval_check(" << kernel_head_params << ") {\n";
+    o << "  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;\n  if (i > mask) return;\n  const u64 domain = mask + 1;\n";
+    for (unsigned b = 0; b <= max_back; b++) o << "  const u32 ib" << b << " = (u32)((i - " << 4 * b << "ull) & mask) << 2;\n";
+    o << body.str();
+    emit_tail(o);
+  } else {
+    o << "__constant__ ColPtrs ccp;\n__constant__ Consts ckc;\n";
+    // choose cuts: first allowed cut point at or after every multiple of parts_m statements
+    std::vector<size_t> bounds{0};
+    for (size_t cp_i : cut_points)
+      if (cp_i >= bounds.back() + (size_t)parts_m) bounds.push_back(cp_i);
+    if (bounds.back() != stmts.size()) bounds.push_back(stmts.size());
+    // definition part of every temporary, and the last part that reads it
+    std::map<unsigned, size_t> def_part, last_use_part;
+    for (size_t p = 0; p + 1 < bounds.size(); p++)
+      for (size_t k = bounds[p]; k < bounds[p + 1]; k++) {
+        def_part[stmts[k].id] = p;
+        for (unsigned u : stmts[k].uses) last_use_part[u] = p;
+      }
+    const size_t FINAL = bounds.size();  // pseudo-part: the kernel tail
+    for (int k = 0; k < 4; k++)
+      if (result.c[k].tid >= 0) last_use_part[(unsigned)result.c[k].tid] = FINAL;
+    std::ostringstream main_body;
+    for (size_t p = 0; p + 1 < bounds.size(); p++) {
+      std::vector<unsigned> ins, outs;
+      std::map<unsigned, bool> seen;
+      for (size_t k = bounds[p]; k < bounds[p + 1]; k++) {
+        for (unsigned u : stmts[k].uses)
+          if (def_part[u] < p && !seen[u]) {
+            seen[u] = true;
+            ins.push_back(u);
+          }
+        if (last_use_part.count(stmts[k].id) && last_use_part[stmts[k].id] > p) outs.push_back(stmts[k].id);
+      }
+      o << "struct PR" << p << " { u32 v[" << (outs.empty() ? 1 : outs.size()) << "]; };\n";
+      o << "static __device__ __noinline__ PR" << p << " part" << p << "(" << ib_params;
+      for (unsigned u : ins) o << ", u32 t" << u;
+      o << ") {\n";
+      for (size_t k = bounds[p]; k < bounds[p + 1]; k++) o << "  const u32 t" << stmts[k].id << " = " << stmts[k].expr << ";\n";
+      o << "  PR" << p << " r;\n";
+      if (outs.empty()) o << "  r.v[0] = 0u;\n";
+      for (size_t j = 0; j < outs.size(); j++) o << "  r.v[" << j << "] = t" << outs[j] << ";\n";
+      o << "  return r;\n}\n";
+      main_body << "  const PR" << p << " r" << p << " = part" << p << "(" << ib_args;
+      for (unsigned u : ins) main_body << ", t" << u;
+      main_body << ");\n";
+      for (size_t j = 0; j < outs.size(); j++) main_body << "  const u32 t" << outs[j] << " = r" << p << ".v[" << j << "];\n";
+    }
+    o << "extern \"C\" __global__ void __launch_bounds__(128, " << min_blocks << ") b2z_eval_check(" << kernel_head_params << ") {\n";
+    o << "  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;\n  if (i > mask) return;\n  const u64 domain = mask + 1;\n";
+    for (unsigned b = 0; b <= max_back; b++) o << "  const u32 ib" << b << " = (u32)((i - " << 4 * b << "ull) & mask) << 2;\n";
+    o << main_body.str();
+    emit_tail(o);
   }
   // ---- witgen: one thread per active trace row; taps read the trace domain (stride 1) ----
   o << "extern \"C\" __global__ void __launch_bounds__(256) b2z_witgen(const __grid_constant__ ColPtrs cp, "
@@ -589,6 +639,11 @@ b2z_err circuit_compile(b2z_ctx* ctx, b2z_circuit* c) {
   B2Z_CUDA(cudaLibraryLoadData(&c->library, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
   B2Z_CUDA(cudaLibraryGetKernel(&c->k_eval_check, c->library, "b2z_eval_check"));
   B2Z_CUDA(cudaLibraryGetKernel(&c->k_witgen, c->library, "b2z_witgen"));
+  if (c->parts_mode) {
+    size_t bytes = 0;
+    B2Z_CUDA(cudaLibraryGetGlobal(&c->ccp_dev, &bytes, c->library, "ccp"));
+    B2Z_CUDA(cudaLibraryGetGlobal(&c->ckc_dev, &bytes, c->library, "ckc"));
+  }
   c->device = ctx->device;
   if (!c->accum_col.empty()) {
     B2Z_CUDA(cudaMalloc(&c->accum_col_dev, 4 * c->accum_col.size()));

@@ -29,6 +29,8 @@ struct b2z_circuit {
   uint64_t source_hash = 0;
   cudaLibrary_t library = nullptr;
   cudaKernel_t k_eval_check = nullptr, k_witgen = nullptr;
+  bool parts_mode = false;                    // eval_check split into __noinline__ parts; tables in module constants
+  void *ccp_dev = nullptr, *ckc_dev = nullptr;  // device addresses of the module's __constant__ tables (parts mode)
   // device-resident tables
   int device = -1;
   uint32_t* accum_col_dev = nullptr;
