@@ -408,8 +408,8 @@ void circuit_codegen(b2z_circuit* c) {
   unsigned max_back = 0;
   for (size_t t = 0; t < c->n_taps; t++) max_back = std::max(max_back, c->tap_back[t]);
   // register cap = 65536 / (128 * min_blocks); tunable for experiments through B2Z_EVALCHECK_MINBLOCKS
-  int min_blocks = 8;
-  if (const char* e = getenv("B2Z_EVALCHECK_MINBLOCKS")) min_blocks = atoi(e) > 0 ? atoi(e) : 8;
+  int min_blocks = 9;
+  if (const char* e = getenv("B2Z_EVALCHECK_MINBLOCKS")) min_blocks = atoi(e) > 0 ? atoi(e) : 9;
   // globals, mix values and the powers of poly_mix are launch constants: they travel by value (constant bank), so
   // they are instruction operands and cost neither loads nor registers
   o << "struct Consts { u32 g[" << (c->globals_size ? c->globals_size : 1) << "]; u32 m[" << (c->mix_size ? c->mix_size : 1)
@@ -418,7 +418,9 @@ void circuit_codegen(b2z_circuit* c) {
   // (cuts right after a constraint has been accumulated, so only the accumulator and the few shared temporaries cross a
   // cut).  The generated CUDA of upstream's rv32im circuit is split the same way; ptxas cannot hoist loads across calls,
   // which is what makes one huge basic block spill.  Tables then live in module-level __constant__ memory.
-  int parts_m = 0;
+  // Measured on B200 (planning circuit, po2 20): straight line 3.79 ms (64 regs + 312 B spills), parts of 60 / 120 / 250 /
+  // 500 statements 2.71 / 2.63 / 2.68 / 2.86 ms, no spills.  Default 120 (B2Z_EVALCHECK_PARTS=0 restores the single block).
+  int parts_m = 120;
   if (const char* e = getenv("B2Z_EVALCHECK_PARTS")) parts_m = atoi(e);
   c->parts_mode = parts_m > 0;
   const std::string cpn = parts_m > 0 ? "ccp" : "cp", kcn = parts_m > 0 ? "ckc" : "kc";
