@@ -120,9 +120,10 @@ def test_full_gpu_pipeline_witgen_to_seal(hal, oracle):
     c.close()
 
 
-@pytest.mark.parametrize("po2", [20, 22])
+@pytest.mark.parametrize("po2", [13, 15, 16, 17, 18, 19, 20, 21, 22])
 def test_baseline_size_segments_verify(hal, po2):
-    """BASELINE.json sizes (po2 = 20 and 22, W = 256): the oracle is too slow here, so use the size-independent
+    """Every segment size between the protocol minimum (po2 = 13) and BASELINE.json's po2 = 20 / 22 (W = 256; each size
+    exercises a different NTT pass plan and FRI round count): the oracle is too slow here, so use the size-independent
     property -- a seal produced from a GPU-generated valid witness must be accepted by the host verifier, must have the
     layout-determined length, and one flipped word must be rejected."""
     sc = S.circuit_planning()

@@ -145,9 +145,17 @@ __device__ __forceinline__ void p2_m_ext_dev(uint32_t* s, uint32_t ones) {
   }
 }
 __device__ __forceinline__ void p2_m_int_dev(uint32_t* s, const P2Consts& k, uint32_t ones) {
-  uint32_t tot = s[0];
+  // pairwise tree (depth 5) instead of a 23-long dependent chain: same 23 adds, shorter critical path
+  uint32_t t8[12];
 #pragma unroll
-  for (int i = 1; i < P2_CELLS; i++) tot = fp_add_p(tot, s[i], ones);
+  for (int i = 0; i < 12; i++) t8[i] = fp_add_p(s[2 * i], s[2 * i + 1], ones);
+  uint32_t t4[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) t4[i] = fp_add_p(t8[2 * i], t8[2 * i + 1], ones);
+  uint32_t t2[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) t2[i] = fp_add_p(t4[2 * i], t4[2 * i + 1], ones);
+  uint32_t tot = fp_add_p(fp_add_p(t2[0], t2[1], ones), t2[2], ones);
 #pragma unroll
   for (int i = 0; i < P2_CELLS; i++) s[i] = fp_add_p(tot, fp_mul_shoup(s[i], k.diag_canon[i], k.diag_shoup[i]), ones);
 }
