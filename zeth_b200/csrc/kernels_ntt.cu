@@ -13,8 +13,8 @@
 //     operands; one uniform twist between the two radix-16 groups of a pass;
 //   * the expand step (out[i] = in[i >> 2]) is folded into the first pass's loads, 1/n and the zk_shift factor
 //     3^rev(j) into the last inverse pass's stores.
-// Columns are processed in chunks sized to stay inside the 126 MB L2, so that the passes after the first one read and
-// write L2-resident lines and HBM sees close to the compulsory traffic (1 read of the input, 1 write of the output).
+// Each pass is one launch over all columns (L2-sized column chunks were measured slower: the passes are instruction
+// bound, not bandwidth bound).
 #include <cuda.h>  // CUtensorMap types only; the encoder is fetched with cudaGetDriverEntryPoint (no libcuda link)
 
 #include <map>
@@ -465,9 +465,12 @@ static void plan_passes(unsigned logn, unsigned* R, unsigned* np) {
 }
 
 static size_t chunk_columns(size_t count, unsigned logn) {
-  // keep one chunk's working set (in place: 4 B * cols * n) around 64 MB so the later passes hit in the 126 MB L2
+  // Optional column chunking (B2Z_NTT_CHUNK_MB).  Keeping a chunk inside the 126 MB L2 was measured NOT to pay: the passes
+  // are instruction bound, and one launch per pass over all columns is fastest (po2 20, 192 columns: 6.1 ms vs 7.2 ms
+  // with 64 MB chunks, 9.7 ms with 16 MB chunks), so the default is a single chunk.
   size_t bytes_per_col = (size_t)4 << logn;
-  size_t c = (64u << 20) / bytes_per_col;
+  static size_t chunk_mb = [] { const char* e = getenv("B2Z_NTT_CHUNK_MB"); return e ? (size_t)atol(e) : (size_t)(1u << 20); }();
+  size_t c = (chunk_mb << 20) / bytes_per_col;
   if (c < 1) c = 1;
   return c < count ? c : count;
 }
