@@ -398,6 +398,61 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(PassArgs a) {
 }
 
 
+
+// First forward pass of an x4 expand (out[i] = in[i >> 2], layers 1-2 skipped): the 16 points of a radix-16 set are
+// 4 input words replicated 4 times, so each thread fetches them with ONE 128-bit load straight from global memory and
+// the tile is never staged for the first radix group.
+template <int R>
+__global__ void __launch_bounds__(256) ntt_expand_first_kernel(PassArgs a) {
+  constexpr int Q2 = R - 4;
+  constexpr unsigned NPTS = 1u << R;
+  constexpr unsigned PITCH_L = NPTS + 1u;
+  constexpr unsigned TILE = NPTS * 32u;
+  constexpr unsigned SETS = 1u << (R - 4);
+  extern __shared__ uint32_t sm[];
+  uint32_t* tws = sm + 32u * (NPTS + 1u);
+  const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t base = (size_t)blockIdx.x * TILE;
+  if (Q2 > 0) {
+    for (unsigned p = tid; p < NPTS; p += blockDim.x) tws[p] = a.group_twist[p];
+    __syncthreads();
+  }
+  const size_t row_start = base + (size_t)lane * NPTS;  // first output element of this lane's row
+  const bool valid = row_start < a.total;
+  const uint4* in4 = reinterpret_cast<const uint4*>(a.in) + (row_start >> 4);
+  uint32_t* lane_base = sm + lane * PITCH_L;
+#pragma unroll
+  for (unsigned set = warp; set < SETS; set += 8) {
+    uint4 q = valid ? __ldg(in4 + set) : make_uint4(0u, 0u, 0u, 0u);
+    uint32_t v[16] = {q.x, q.x, q.x, q.x, q.y, q.y, q.y, q.y, q.z, q.z, q.z, q.z, q.w, q.w, q.w, q.w};
+    dit_base<4, 3>(v);
+    const unsigned p0 = set << 4;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      uint32_t x = v[j];
+      if (Q2 > 0) x = fp_mul(x, tws[p0 + j]);
+      lane_base[p0 + j] = x;
+    }
+  }
+  __syncthreads();
+  if (Q2 > 0) {
+    radix_group<R, (Q2 > 0 ? Q2 : 1), 4, true, false, 1, false>(sm, tws, lane, warp, 8);
+    __syncthreads();
+  }
+  // store: element e = tid + 256 k -> row (tid >> R) + k * 2^(8-R), column tid & (NPTS - 1)
+  constexpr unsigned K = TILE / 256;
+  const unsigned sidx0 = (tid >> R) * PITCH_L + (tid & (NPTS - 1));
+  constexpr unsigned SSTEP = (256u >> R) * PITCH_L;
+  uint32_t* dst = a.out + base + tid;
+  if (base + TILE <= a.total) {
+#pragma unroll 8
+    for (unsigned k = 0; k < K; k++) dst[(size_t)k * 256] = sm[sidx0 + k * SSTEP];
+  } else {
+    for (unsigned k = 0; k < K; k++)
+      if (base + tid + (size_t)k * 256 < a.total) dst[(size_t)k * 256] = sm[sidx0 + k * SSTEP];
+  }
+}
+
 // Strided pass with TMA staging (in place).  Same arithmetic as ntt_pass_kernel<INV, 1, R, false>.
 template <bool INV, int R>
 __global__ void __launch_bounds__(256) ntt_pass_tma_kernel(const __grid_constant__ CUtensorMap tmap, PassArgs a) {
@@ -531,6 +586,22 @@ static b2z_err launch_tma(b2z_ctx* ctx, const PassArgs& a) {
 template <bool INV, int FIRST>
 static b2z_err launch_one(b2z_ctx* ctx, const PassArgs& a, unsigned R) {
   const bool rows = (a.s_lo == 0);
+  // first pass of an x4 expand: dedicated kernel (128-bit loads of the 4 distinct words of every radix-16 set)
+  if (rows && !INV && FIRST == 3 && a.ebits == 2 && R >= 4 && R <= 8 && (reinterpret_cast<uintptr_t>(a.in) & 15) == 0) {
+    size_t tile_elems = (size_t)32 << R;
+    size_t tiles = (a.total + tile_elems - 1) / tile_elems;
+    size_t smem = sizeof(uint32_t) * (32 * ((1u << R) + 1) + (1u << R));
+    switch (R) {
+      case 4: ntt_expand_first_kernel<4><<<(unsigned)tiles, 256, smem, ctx->stream>>>(a); break;
+      case 5: ntt_expand_first_kernel<5><<<(unsigned)tiles, 256, smem, ctx->stream>>>(a); break;
+      case 6: ntt_expand_first_kernel<6><<<(unsigned)tiles, 256, smem, ctx->stream>>>(a); break;
+      case 7: ntt_expand_first_kernel<7><<<(unsigned)tiles, 256, smem, ctx->stream>>>(a); break;
+      default: ntt_expand_first_kernel<8><<<(unsigned)tiles, 256, smem, ctx->stream>>>(a); break;
+    }
+    ctx->launches++;
+    B2Z_CUDA(cudaGetLastError());
+    return nullptr;
+  }
   // strided in-place passes with >= 128-byte aligned rows go through TMA
   if (!rows && a.in == a.out && tma_enabled() && R >= 4 && (a.total >> (a.s_lo + R)) < (1ull << 31)) {
     switch (R) {
