@@ -197,9 +197,12 @@ __device__ __forceinline__ void radix_group(uint32_t* sm, const uint32_t* tws, u
   constexpr unsigned PITCH_L = ROWS ? ((1u << R) + 1u) : 1u;
   constexpr unsigned SETS = 1u << (R - Q);
   uint32_t* lane_base = sm + lane * PITCH_L;
-  (void)nwarps;  // kernels always run 8 warps; a compile-time stride lets the set loop unroll (no stack-resident v[])
+  (void)nwarps;  // kernels always run 8 warps: the set loop has a compile-time trip count (no select/move code, no stack v[])
+  constexpr unsigned ITER = SETS >= 8 ? SETS / 8 : 1;
 #pragma unroll
-  for (unsigned set = warp; set < SETS; set += 8) {
+  for (unsigned it = 0; it < ITER; it++) {
+    const unsigned set = warp + 8 * it;
+    if (SETS < 8 && set >= SETS) break;
     // set index -> the point bits outside [G_LO, G_LO+Q)
     const unsigned low = set & ((1u << G_LO) - 1), high = set >> G_LO;
     const unsigned p0 = (high << (G_LO + Q)) | low;
@@ -421,8 +424,11 @@ __global__ void __launch_bounds__(256) ntt_expand_first_kernel(PassArgs a) {
   const bool valid = row_start < a.total;
   const uint4* in4 = reinterpret_cast<const uint4*>(a.in) + (row_start >> 4);
   uint32_t* lane_base = sm + lane * PITCH_L;
+  constexpr unsigned ITER = SETS >= 8 ? SETS / 8 : 1;
 #pragma unroll
-  for (unsigned set = warp; set < SETS; set += 8) {
+  for (unsigned it = 0; it < ITER; it++) {
+    const unsigned set = warp + 8 * it;
+    if (SETS < 8 && set >= SETS) break;
     uint4 q = valid ? __ldg(in4 + set) : make_uint4(0u, 0u, 0u, 0u);
     uint32_t v[16] = {q.x, q.x, q.x, q.x, q.y, q.y, q.y, q.y, q.z, q.z, q.z, q.z, q.w, q.w, q.w, q.w};
     dit_base<4, 3>(v);
