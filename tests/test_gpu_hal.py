@@ -195,3 +195,39 @@ def test_poly_divide(hal, oracle, count):
     recon = (shifted - zq) % P
     assert np.array_equal(recon.astype(np.uint32), p.reshape(count, 4))
     assert not q[-1].any()
+
+
+def test_full_size_properties_po2_22(hal):
+    """BASELINE full size (po2 = 22, LDE domain 2^24) without the oracle: linearity of the expand-NTT,
+    interpolate(evaluate(x)) == x on the full LDE domain, and hash_rows depending only on its own row."""
+    rng = np.random.default_rng(2200)
+    po2 = 22
+    n = 1 << po2
+    a, b = rand_fp(rng, n), rand_fp(rng, n)
+    s = ((a.astype(np.uint64) + b) % P).astype(np.uint32)
+    da, db, ds = hal.copy_from(a), hal.copy_from(b), hal.copy_from(s)
+    la, lb, ls = hal.alloc(4 * n), hal.alloc(4 * n), hal.alloc(4 * n)
+    for src, dst in ((da, la), (db, lb), (ds, ls)):
+        hal.batch_expand_into_evaluate_ntt(dst, src, 1, po2, 2)
+    hal.eltwise_add_elem(la, la, lb, 4 * n)
+    assert np.array_equal(hal.view(la, 4 * n), hal.view(ls, 4 * n))  # NTT(a) + NTT(b) == NTT(a + b)
+    # round trip on the full LDE domain: interpolate(evaluate(x)) == x for bit-reversed-coefficient input x
+    x = rand_fp(rng, 4 * n)
+    dx = hal.copy_from(x)
+    hal.batch_evaluate_ntt(dx, 1, po2 + 2, 0)
+    hal.batch_interpolate_ntt(dx, 1, po2 + 2)
+    assert np.array_equal(hal.view(dx, 4 * n), x)
+    # hash_rows: digest of row r depends only on row r (compare a 2-column matrix with a row-permuted copy)
+    rows = 1 << 16
+    m = rand_fp(rng, 2 * rows)
+    perm = rng.permutation(rows)
+    mp = np.concatenate([m[:rows][perm], m[rows:][perm]])
+    dm, dmp = hal.copy_from(m), hal.copy_from(mp)
+    o1, o2 = hal.alloc(8 * rows), hal.alloc(8 * rows)
+    hal.hash_rows(o1, dm, rows, 2)
+    hal.hash_rows(o2, dmp, rows, 2)
+    h1 = hal.view(o1, 8 * rows).reshape(rows, 8)
+    h2 = hal.view(o2, 8 * rows).reshape(rows, 8)
+    assert np.array_equal(h1[perm], h2)
+    for p in (da, db, ds, la, lb, ls, dx, dm, dmp, o1, o2):
+        hal.free(p)
