@@ -351,11 +351,12 @@ def run_b2z(args):
                     traffic = ent["dram_bytes"]
         except Exception:
             pass
-        roofline = {"kernel": "hash_rows_kernel (Poseidon2 leaves, data group LDE)", "bound": "hbm", "achieved": bytes_hr / ms_hr / 1e6,
+        roofline = {"kernel": "hash_rows_mixed_kernel (Poseidon2 leaves of the data-group LDE; INT + exact-FP64 instruction streams)", "bound": "hbm", "achieved": bytes_hr / ms_hr / 1e6,
                     "peak": hbm, "unit": "GB/s", "frac": bytes_hr / ms_hr / 1e6 / hbm, "traffic": traffic, "peak_source": peak_src,
                     "ms_per_launch": ms_hr, "algorithmic_bytes": bytes_hr,
-                    "alu_note": "INT32-pipe bound, not HBM bound: 1356 modular products per 64 B absorbed; measured product peak "
-                                "3.63e12/s (tools/microbench/intpipe.cu) => hard ceiling 2.7e9 permutations/s",
+                    "alu_note": "arithmetic-pipe bound, not HBM bound: 1356 modular products per 64 B absorbed; measured INT32 product "
+                                "peak 3.63e12/s (tools/microbench/intpipe.cu) => 2.7e9 permutations/s for the integer stream alone; "
+                                "half of the CTAs run the permutation as exact FP64 arithmetic on the FP64 pipe (DESIGN.md 4.0)",
                     "alu_frac_of_product_peak": 1356 * perms / (ms_hr * 1e-3) / 3.63e12,
                     "poseidon2_perms_per_s": perms / (ms_hr * 1e-3), "modmul_per_s": 1356 * perms / (ms_hr * 1e-3)}
         ms_ex = time_kernel(lambda: hal.batch_expand_into_evaluate_ntt(lde.data_ptr(), d_data.data_ptr(), wd, po2, 2))

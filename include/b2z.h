@@ -134,6 +134,8 @@ const char* b2z_phase_name(size_t i);
 
 /* host-side Poseidon2 (transcript) helpers, exported for tests: hash_elem_slice / hash_pair / permutation */
 void b2z_host_poseidon2_mix(uint32_t* state24);
+/* the same permutation computed by the exact-FP64 instruction stream the mixed hash kernels co-schedule (host copy) */
+void b2z_host_poseidon2_mix_f64(uint32_t* state24);
 void b2z_host_hash_elem_slice(const uint32_t* elems, size_t n, uint32_t* digest8);
 
 #ifdef __cplusplus

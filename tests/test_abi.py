@@ -102,3 +102,29 @@ def test_product_verifier_matches_oracle_verifier(oracle):
             assert c.verify(bad) == oc.verify(bad) != 0
         assert c.verify(seal[:-3]) == oc.verify(seal[:-3]) != 0
         c.close()
+
+
+def test_host_poseidon2_f64_stream_is_bit_exact():
+    """The exact-FP64 instruction stream of the mixed hash kernels (poseidon2_f64.cuh), host copy: same words as the
+    integer permutation on random, all-zero, all-(P-1) and sparse states."""
+    import ctypes as C
+
+    import numpy as np
+    from zeth_b200 import build
+
+    L = C.CDLL(build.build())
+    P = 15 * (1 << 27) + 1
+    rng = np.random.default_rng(2024)
+    for it in range(300):
+        st = rng.integers(0, P, 24, dtype=np.uint64).astype(np.uint32)
+        if it == 0:
+            st[:] = 0
+        elif it == 1:
+            st[:] = P - 1
+        elif it == 2:
+            st[:] = 0
+            st[5] = 1
+        a, b = st.copy(), st.copy()
+        L.b2z_host_poseidon2_mix(a.ctypes.data_as(C.c_void_p))
+        L.b2z_host_poseidon2_mix_f64(b.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(a, b)

@@ -231,3 +231,36 @@ def test_full_size_properties_po2_22(hal):
     assert np.array_equal(h1[perm], h2)
     for p in (da, db, ds, la, lb, ls, dx, dm, dmp, o1, o2):
         hal.free(p)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("period,n_int", [(1, 0), (3, 2), (2, 1), (1, 1)])
+@pytest.mark.parametrize("rows,cols", [(1 << 12, 40), (1 << 13, 16), (96, 5), (1 << 12, 0)])
+def test_hash_rows_mixed_streams(hal, oracle, monkeypatch, rows, cols, period, n_int):
+    """The mixed INT / FP64 leaf kernel (kernels_hash.cu): all-FP64, 2:1, 1:1 and all-INT role ratios give the oracle's digests."""
+    monkeypatch.setenv("B2Z_HASH_MIXED_MIN_ROWS", "0")
+    monkeypatch.setenv("B2Z_HASH_ROLE_PERIOD", str(period))
+    monkeypatch.setenv("B2Z_HASH_ROLE_INT", str(n_int))
+    rng = np.random.default_rng(rows * 31 + cols)
+    m = rand_fp(rng, rows * cols)
+    if cols:
+        m[:rows] = np.where(np.arange(rows) % 3 == 0, P - 1, m[:rows])  # edge values in the first column
+        m[rows - 1 :: rows] = 0
+    dm = hal.copy_from(m) if cols else hal.alloc(1)
+    do = hal.alloc(8 * rows)
+    hal.hash_rows(do, dm, rows, cols)
+    assert np.array_equal(hal.view(do, 8 * rows), oracle.hash_rows(m, rows, cols))
+    hal.free(dm)
+    hal.free(do)
+
+
+@pytest.mark.gpu
+def test_hash_rows_mixed_default_large(hal, oracle):
+    """Default launch configuration at a size where the mixed kernel is the one that runs (2^20 rows)."""
+    rows, cols = 1 << 20, 16
+    m = rand_fp(np.random.default_rng(77), rows * cols)
+    dm, do = hal.copy_from(m), hal.alloc(8 * rows)
+    hal.hash_rows(do, dm, rows, cols)
+    assert np.array_equal(hal.view(do, 8 * rows), oracle.hash_rows(m, rows, cols))
+    hal.free(dm)
+    hal.free(do)

@@ -29,7 +29,11 @@ WANT = [
     ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "st_math"),
     ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "st_wait"),
     ("smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "st_notsel"),
+    ("smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio", "st_noinst"),
+    ("smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio", "st_dispatch"),
+    ("smsp__average_warps_issue_stalled_imc_miss_per_issue_active.ratio", "st_imc"),
 ]
+PIPES = "--pipes" in sys.argv  # also list every per-pipe utilisation column the report has
 out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr, units = rows[0], rows[1]
@@ -46,3 +50,13 @@ for r in rows[2:]:
                 pass
             parts.append(f"{short}={v}{units[idx[key]] if short in ('time', 'dram_rd', 'dram_wr') else ''}")
     print("   " + "  ".join(parts))
+    if PIPES:
+        pp = []
+        for h, i in idx.items():
+            if ("pipe_" in h) and ("pct" in h) and r[i] not in ("", "0", "n/a"):
+                try:
+                    if float(r[i]) >= 0.5:
+                        pp.append(f"{h.replace('.avg.pct_of_peak_sustained_active', '').replace('sm__', '')}={float(r[i]):.3g}")
+                except ValueError:
+                    pass
+        print("   pipes: " + "  ".join(pp))

@@ -32,7 +32,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for src in sources():
         obj = os.path.join(HERE, "build", os.path.basename(src) + ".o")
         cmd = [NVCC, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-ccbin", "/usr/bin/g++",
-               "-Xcompiler", "-fPIC", "-c", src, "-o", obj]
+               "-Xcompiler", "-fPIC,-ffp-contract=off,-mfma", "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

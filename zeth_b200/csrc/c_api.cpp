@@ -60,6 +60,7 @@ b2z_err b2z_destroy(b2z_ctx* ctx) {
   for (int i = 0; i <= MAX_PO2; i++)
     if (ctx->pow3rev[i]) cudaFree(ctx->pow3rev[i]);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->hash_sched) cudaFree(ctx->hash_sched);
   for (auto& pr : ctx->phase_events) {
     cudaEventDestroy(pr.first);
     cudaEventDestroy(pr.second);
@@ -277,6 +278,7 @@ int b2z_verify_segment(const b2z_circuit* c, const uint32_t* seal, size_t seal_w
   return verify_segment(c, seal, seal_words);
 }
 void b2z_host_poseidon2_mix(uint32_t* s) { host_poseidon2_mix(s); }
+void b2z_host_poseidon2_mix_f64(uint32_t* s) { host_poseidon2_mix_f64(s); }
 void b2z_host_hash_elem_slice(const uint32_t* e, size_t n, uint32_t* d) { host_hash_elem_slice(e, n, d); }
 
 }  // extern "C"

@@ -46,6 +46,7 @@ struct b2z_ctx {
   uint64_t launches = 0;
   // per-size device table, built lazily: 3^rev(j) for zk_shift (NTT twist tables live in kernels_ntt.cu's registry)
   uint32_t* pow3rev[b2z::MAX_PO2 + 1] = {};
+  unsigned* hash_sched = nullptr;  // tile queue + per-SM role counters of the mixed INT/FP64 hash kernels
   // pinned staging for small transcript round trips
   uint32_t* pinned = nullptr;
   size_t pinned_words = 0;
@@ -96,6 +97,7 @@ b2z_err launch_gather_queries(b2z_ctx* ctx, uint32_t* seal_dev, const GatherTree
 
 // host Poseidon2 / transcript (transcript.cpp)
 void host_poseidon2_mix(uint32_t* state24);
+void host_poseidon2_mix_f64(uint32_t* state24);  // same permutation through the FP64 instruction stream
 void host_hash_elem_slice(const uint32_t* in, size_t n, uint32_t* digest);
 void host_hash_pair(const uint32_t* a, const uint32_t* b, uint32_t* digest);
 struct HostRng {

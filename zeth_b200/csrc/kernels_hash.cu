@@ -10,10 +10,12 @@
 #include "common.h"
 #include "poseidon2.cuh"
 #include "poseidon2_consts.h"
+#include "poseidon2_f64.cuh"
 
 namespace b2z {
 
 __constant__ P2Consts c_p2;
+__constant__ P2ConstsF64 c_p2f;
 static bool g_p2_uploaded[16] = {};
 
 static b2z_err upload_consts(b2z_ctx* ctx) {
@@ -22,6 +24,8 @@ static b2z_err upload_consts(b2z_ctx* ctx) {
   if (ctx->device < 16 && g_p2_uploaded[ctx->device]) return nullptr;
   const P2Consts& h = p2_host_consts();
   B2Z_CUDA(cudaMemcpyToSymbol(c_p2, &h, sizeof(P2Consts), 0, cudaMemcpyHostToDevice));
+  const P2ConstsF64& hf = p2_host_consts_f64();
+  B2Z_CUDA(cudaMemcpyToSymbol(c_p2f, &hf, sizeof(P2ConstsF64), 0, cudaMemcpyHostToDevice));
   if (ctx->device < 16) g_p2_uploaded[ctx->device] = true;
   return nullptr;
 }
@@ -50,6 +54,91 @@ __global__ void __launch_bounds__(THREADS, MINB) hash_rows_kernel(uint32_t* __re
   uint4* o = reinterpret_cast<uint4*>(out + 8 * r);
   o[0] = make_uint4(s[0], s[1], s[2], s[3]);
   o[1] = make_uint4(s[4], s[5], s[6], s[7]);
+}
+
+// ---- mixed INT / FP64 leaf hashing ----
+// One persistent launch; every warp pulls 32-row tiles from a global counter until none are left.  A CTA is either
+// an INT CTA (poseidon2.cuh: IMAD + ALU pipes) or an FP64 CTA (poseidon2_f64.cuh: DFMA pipe only); the role comes
+// from a per-SM arrival counter so that every SM hosts both kinds in the ratio n_int : (period - n_int).  The two
+// instruction streams produce identical digests, so which warp hashed a row is unobservable; the dynamic tile queue
+// balances their different speeds.  sched[0] = tile counter, sched[1 + smid] = CTA arrival counter of that SM.
+constexpr int HASH_SCHED_WORDS = 1 + 512;
+
+__device__ __forceinline__ double p2f_reduce(double x) {  // |x| < 2^38 -> (-0.51 P, 0.51 P)
+  double q = __dadd_rn(__fma_rn(x, F64_INVP, F64_MAGIC), -F64_MAGIC);
+  return __fma_rn(q, -F64_P, x);
+}
+
+// both row routines keep a single call site of their permutation (tail columns are predicated loads of 0)
+__device__ __forceinline__ void hash_row_int(uint32_t* __restrict__ out, const uint32_t* __restrict__ matrix, size_t rows, size_t cols, size_t r,
+                                             uint32_t ones) {
+  uint32_t s[P2_CELLS];
+#pragma unroll
+  for (int i = 0; i < P2_CELLS; i++) s[i] = 0;
+  const uint32_t* p = matrix + r;
+  const size_t nblk = cols == 0 ? 1 : (cols + P2_RATE - 1) / P2_RATE;
+#pragma unroll 1
+  for (size_t blk = 0; blk < nblk; blk++) {
+    const unsigned left = (unsigned)min(cols - blk * P2_RATE, (size_t)P2_RATE);  // columns in this block (0 only when cols == 0)
+#pragma unroll
+    for (int i = 0; i < P2_RATE; i++) {
+      s[i] = (unsigned)i < left ? __ldg(p) : 0u;
+      p += rows;
+    }
+    p2_permute_dev_compact(s, c_p2, ones);
+  }
+  uint4* o = reinterpret_cast<uint4*>(out + 8 * r);
+  o[0] = make_uint4(s[0], s[1], s[2], s[3]);
+  o[1] = make_uint4(s[4], s[5], s[6], s[7]);
+}
+
+__device__ __forceinline__ void hash_row_f64(uint32_t* __restrict__ out, const uint32_t* __restrict__ matrix, size_t rows, size_t cols, size_t r) {
+  double s[P2_CELLS];
+#pragma unroll
+  for (int i = 0; i < P2_CELLS; i++) s[i] = 0.0;
+  const uint32_t* p = matrix + r;
+  const size_t nblk = cols == 0 ? 1 : (cols + P2_RATE - 1) / P2_RATE;
+#pragma unroll 1
+  for (size_t blk = 0; blk < nblk; blk++) {
+    const unsigned left = (unsigned)min(cols - blk * P2_RATE, (size_t)P2_RATE);
+#pragma unroll
+    for (int i = 0; i < P2_RATE; i++) {
+      s[i] = p2f_from_mont((unsigned)i < left ? __ldg(p) : 0u);
+      p += rows;
+    }
+#pragma unroll
+    for (int i = P2_RATE; i < P2_CELLS; i++) s[i] = p2f_reduce(s[i]);  // carried capacity cells back below 2^31
+    p2f_permute(s, c_p2f);
+  }
+  uint4* o = reinterpret_cast<uint4*>(out + 8 * r);
+  o[0] = make_uint4(p2f_to_mont(s[0]), p2f_to_mont(s[1]), p2f_to_mont(s[2]), p2f_to_mont(s[3]));
+  o[1] = make_uint4(p2f_to_mont(s[4]), p2f_to_mont(s[5]), p2f_to_mont(s[6]), p2f_to_mont(s[7]));
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) hash_rows_mixed_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ matrix, size_t rows,
+                                                                    size_t cols, uint32_t ones, unsigned* __restrict__ sched, unsigned n_tiles,
+                                                                    unsigned period, unsigned n_int) {
+  __shared__ unsigned s_role;
+  if (threadIdx.x == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    s_role = atomicAdd(&sched[1 + (smid & 511)], 1u) % period;
+  }
+  __syncthreads();
+  const bool f64_role = s_role >= n_int;
+  const unsigned lane = threadIdx.x & 31;
+  for (;;) {
+    unsigned tile = 0;
+    if (lane == 0) tile = atomicAdd(&sched[0], 1u);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    if (tile >= n_tiles) break;
+    size_t r = (size_t)tile * 32 + lane;
+    if (r < rows) {
+      if (f64_role) hash_row_f64(out, matrix, rows, cols, r);
+      else hash_row_int(out, matrix, rows, cols, r, ones);
+    }
+  }
 }
 
 __global__ void __launch_bounds__(128) hash_fold_kernel(uint32_t* __restrict__ nodes, size_t in_size, size_t out_size, uint32_t ones) {
@@ -90,17 +179,31 @@ b2z_err launch_hash_fold_top(b2z_ctx* ctx, uint32_t* nodes, size_t start_out) {
   return nullptr;
 }
 
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
 b2z_err launch_hash_rows(b2z_ctx* ctx, uint32_t* out, const uint32_t* matrix, size_t rows, size_t cols) {
   if (rows == 0) return nullptr;
   B2Z_TRY(upload_consts(ctx));
-  // launch-shape experiments: B2Z_HASH_VARIANT = 0 (128 threads, compiler-chosen registers) | 1 (<= 48 regs) | 2 (<= 40 regs) | 3 (256 threads)
-  static int variant = [] { const char* e = getenv("B2Z_HASH_VARIANT"); return e ? atoi(e) : 0; }();
-  switch (variant) {
-    case 1: hash_rows_kernel<128, 10><<<(unsigned)((rows + 127) / 128), 128, 0, ctx->stream>>>(out, matrix, rows, cols, 0xffffffffu); break;
-    case 2: hash_rows_kernel<128, 12><<<(unsigned)((rows + 127) / 128), 128, 0, ctx->stream>>>(out, matrix, rows, cols, 0xffffffffu); break;
-    case 3: hash_rows_kernel<256, 4><<<(unsigned)((rows + 255) / 256), 256, 0, ctx->stream>>>(out, matrix, rows, cols, 0xffffffffu); break;
-    case 4: hash_rows_kernel<64, 16><<<(unsigned)((rows + 63) / 64), 64, 0, ctx->stream>>>(out, matrix, rows, cols, 0xffffffffu); break;
-    default: hash_rows_kernel<128, 1><<<(unsigned)((rows + 127) / 128), 128, 0, ctx->stream>>>(out, matrix, rows, cols, 0xffffffffu); break;
+  // B2Z_HASH_MIXED=0 forces the INT-only kernel; the mixed kernel needs enough rows to fill the persistent grid
+  // (read per call so that tests and sweeps can switch modes inside one process)
+  const int mixed = env_int("B2Z_HASH_MIXED", 1);
+  const int ctas_per_sm = env_int("B2Z_HASH_CTAS", 6);          // resident CTAs per SM: 6 (80 regs), 7 (72), 8 (64, spills)
+  const int period = env_int("B2Z_HASH_ROLE_PERIOD", 2);        // of every `period` CTAs on an SM ...
+  const int n_int = env_int("B2Z_HASH_ROLE_INT", 1);            // ... this many run the INT stream, the rest FP64
+  const size_t grid = (size_t)ctx->sm_count * ctas_per_sm;
+  const size_t min_rows = (size_t)env_int("B2Z_HASH_MIXED_MIN_ROWS", (int)(grid * 128 * 4));
+  if (mixed && period >= 1 && rows >= min_rows && rows / 32 < 0xffffffffu) {
+    if (!ctx->hash_sched) B2Z_CUDA(cudaMalloc(&ctx->hash_sched, HASH_SCHED_WORDS * sizeof(unsigned)));
+    B2Z_CUDA(cudaMemsetAsync(ctx->hash_sched, 0, HASH_SCHED_WORDS * sizeof(unsigned), ctx->stream));
+    unsigned n_tiles = (unsigned)((rows + 31) / 32);
+    auto kern = ctas_per_sm >= 8 ? hash_rows_mixed_kernel<8> : ctas_per_sm == 7 ? hash_rows_mixed_kernel<7> : hash_rows_mixed_kernel<6>;
+    kern<<<(unsigned)grid, 128, 0, ctx->stream>>>(out, matrix, rows, cols, 0xffffffffu, ctx->hash_sched, n_tiles, (unsigned)period,
+                                                  (unsigned)n_int);
+  } else {
+    hash_rows_kernel<128, 1><<<(unsigned)((rows + 127) / 128), 128, 0, ctx->stream>>>(out, matrix, rows, cols, 0xffffffffu);
   }
   ctx->launches++;
   B2Z_CUDA(cudaGetLastError());

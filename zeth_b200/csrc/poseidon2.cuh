@@ -181,6 +181,28 @@ __device__ __forceinline__ void p2_permute_dev(uint32_t* s, const P2Consts& k, u
     p2_m_ext_dev(s, ones);
   }
 }
+// Same permutation with ONE copy of each layer in the instruction stream (E; [21 x P after the 5th E]; S, nine times):
+// ~14 KB of SASS instead of ~30 KB, so that it shares the SM's instruction cache with the FP64 stream
+// (poseidon2_f64.cuh) in the mixed hash kernels.
+__device__ __forceinline__ void p2_permute_dev_compact(uint32_t* s, const P2Consts& k, uint32_t ones) {
+  const int32_t* rc = k.rc_minus_p;
+#pragma unroll 1
+  for (int e = 0; e < 2 * P2_ROUNDS_HALF_FULL + 1; e++) {
+    p2_m_ext_dev(s, ones);
+    if (e == 2 * P2_ROUNDS_HALF_FULL) break;
+    if (e == P2_ROUNDS_HALF_FULL) {
+#pragma unroll 1
+      for (int r = 0; r < P2_ROUNDS_PARTIAL; r++) {
+        s[0] = p2_sbox_rc(s[0], rc[r], ones);
+        p2_m_int_dev(s, k, ones);
+      }
+      rc += P2_ROUNDS_PARTIAL;
+    }
+#pragma unroll
+    for (int i = 0; i < P2_CELLS; i++) s[i] = p2_sbox_rc(s[i], rc[i], ones);
+    rc += P2_CELLS;
+  }
+}
 #endif
 
 B2Z_HD void p2_permute(uint32_t* s, const P2Consts& k) {

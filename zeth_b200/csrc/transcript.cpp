@@ -9,6 +9,7 @@
 #include "common.h"
 #include "poseidon2.cuh"
 #include "poseidon2_consts.h"
+#include "poseidon2_f64.cuh"
 
 namespace b2z {
 
@@ -31,6 +32,27 @@ const P2Consts& p2_host_consts() {
 }
 
 void host_poseidon2_mix(uint32_t* s) { p2_permute(s, p2_host_consts()); }
+
+// constants of the FP64 instruction stream (poseidon2_f64.cuh): plain residues as doubles
+const P2ConstsF64& p2_host_consts_f64() {
+  static P2ConstsF64 k = [] {
+    P2ConstsF64 c;
+    for (int i = 0; i < P2_NUM_RC; i++) c.rc[i] = (double)P2_ROUND_CONSTANTS[i];
+    for (int i = 0; i < P2_CELLS; i++) {
+      c.diag[i] = (double)P2_M_INT_DIAG[i];
+      c.diag_over_p[i] = (double)P2_M_INT_DIAG[i] / F64_P;
+    }
+    return c;
+  }();
+  return k;
+}
+// the permutation through the FP64 stream, Montgomery words in and out (host copy of what the FP64 warps run)
+void host_poseidon2_mix_f64(uint32_t* s) {
+  double d[P2_CELLS];
+  for (int i = 0; i < P2_CELLS; i++) d[i] = p2f_from_mont(s[i]);
+  p2f_permute(d, p2_host_consts_f64());
+  for (int i = 0; i < P2_CELLS; i++) s[i] = p2f_to_mont(d[i]);
+}
 
 void host_hash_elem_slice(const uint32_t* in, size_t n, uint32_t* digest) {
   uint32_t st[P2_CELLS] = {};
