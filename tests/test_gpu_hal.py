@@ -264,3 +264,35 @@ def test_hash_rows_mixed_default_large(hal, oracle):
     assert np.array_equal(hal.view(do, 8 * rows), oracle.hash_rows(m, rows, cols))
     hal.free(dm)
     hal.free(do)
+
+
+@pytest.mark.parametrize("period,n_int", [(1, 0), (2, 1), (3, 1)])
+def test_merkle_build_mixed_streams(hal, oracle, monkeypatch, period, n_int):
+    """Leaves and interior layers through the mixed INT / FP64 kernels at every size (threshold forced to 0)."""
+    monkeypatch.setenv("B2Z_HASH_MIXED_MIN_ROWS", "0")
+    monkeypatch.setenv("B2Z_HASH_ROLE_PERIOD", str(period))
+    monkeypatch.setenv("B2Z_HASH_ROLE_INT", str(n_int))
+    rows, cols = 4096, 21
+    m = rand_fp(np.random.default_rng(900 + period), rows * cols)
+    d = hal.copy_from(m)
+    nodes = hal.copy_from(np.zeros(2 * rows * 8, dtype=np.uint32))
+    hal.merkle_build(nodes, d, rows, cols)
+    got = hal.view(nodes, 2 * rows * 8)
+    want = oracle.merkle_nodes(m, rows, cols)
+    hal.free(d)
+    hal.free(nodes)
+    assert np.array_equal(got[8:], want[8:])
+
+
+def test_merkle_build_mixed_default_large(hal, oracle):
+    """2^20 leaves: the bottom interior layers run the mixed fold kernel in its default configuration."""
+    rows, cols = 1 << 20, 3
+    m = rand_fp(np.random.default_rng(901), rows * cols)
+    d = hal.copy_from(m)
+    nodes = hal.copy_from(np.zeros(2 * rows * 8, dtype=np.uint32))
+    hal.merkle_build(nodes, d, rows, cols)
+    got = hal.view(nodes, 2 * rows * 8)
+    want = oracle.merkle_nodes(m, rows, cols)
+    hal.free(d)
+    hal.free(nodes)
+    assert np.array_equal(got[8:], want[8:])

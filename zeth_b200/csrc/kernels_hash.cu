@@ -69,7 +69,17 @@ __device__ __forceinline__ double p2f_reduce(double x) {  // |x| < 2^38 -> (-0.5
   return __fma_rn(q, -F64_P, x);
 }
 
-// both row routines keep a single call site of their permutation (tail columns are predicated loads of 0)
+// both row routines keep a single call site of their permutation (tail columns are predicated loads of 0).
+// The guarded load is spelled in PTX: left to itself the compiler widens the guard to 64 bits and rebuilds every
+// address from scratch (9 instructions per column) -- code size matters here, see the instruction-cache note above.
+__device__ __forceinline__ uint32_t ld_col_guarded(const uint32_t* p, unsigned i, unsigned left) {
+  uint32_t v;
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.lt.u32 q, %2, %3;\n\tmov.u32 %0, 0;\n\t@q ld.global.nc.u32 %0, [%1];\n\t}"
+      : "=r"(v)
+      : "l"(p), "r"(i), "r"(left));
+  return v;
+}
 __device__ __forceinline__ void hash_row_int(uint32_t* __restrict__ out, const uint32_t* __restrict__ matrix, size_t rows, size_t cols, size_t r,
                                              uint32_t ones) {
   uint32_t s[P2_CELLS];
@@ -82,7 +92,7 @@ __device__ __forceinline__ void hash_row_int(uint32_t* __restrict__ out, const u
     const unsigned left = (unsigned)min(cols - blk * P2_RATE, (size_t)P2_RATE);  // columns in this block (0 only when cols == 0)
 #pragma unroll
     for (int i = 0; i < P2_RATE; i++) {
-      s[i] = (unsigned)i < left ? __ldg(p) : 0u;
+      s[i] = ld_col_guarded(p, (unsigned)i, left);
       p += rows;
     }
     p2_permute_dev_compact(s, c_p2, ones);
@@ -103,7 +113,7 @@ __device__ __forceinline__ void hash_row_f64(uint32_t* __restrict__ out, const u
     const unsigned left = (unsigned)min(cols - blk * P2_RATE, (size_t)P2_RATE);
 #pragma unroll
     for (int i = 0; i < P2_RATE; i++) {
-      s[i] = p2f_from_mont((unsigned)i < left ? __ldg(p) : 0u);
+      s[i] = p2f_from_mont(ld_col_guarded(p, (unsigned)i, left));
       p += rows;
     }
 #pragma unroll
@@ -151,6 +161,55 @@ __global__ void __launch_bounds__(128) hash_fold_kernel(uint32_t* __restrict__ n
   uint4* o = reinterpret_cast<uint4*>(nodes + 8 * (out_size + j));
   o[0] = make_uint4(s[0], s[1], s[2], s[3]);
   o[1] = make_uint4(s[4], s[5], s[6], s[7]);
+}
+
+// Merkle interior layer with the same two streams: a tile is 32 parents, one per lane.
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) hash_fold_mixed_kernel(uint32_t* __restrict__ nodes, size_t in_size, size_t out_size, uint32_t ones,
+                                                                    unsigned* __restrict__ sched, unsigned n_tiles, unsigned period, unsigned n_int) {
+  __shared__ unsigned s_role;
+  if (threadIdx.x == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    s_role = atomicAdd(&sched[1 + (smid & 511)], 1u) % period;
+  }
+  __syncthreads();
+  const bool f64_role = s_role >= n_int;
+  const unsigned lane = threadIdx.x & 31;
+  for (;;) {
+    unsigned tile = 0;
+    if (lane == 0) tile = atomicAdd(&sched[0], 1u);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    if (tile >= n_tiles) break;
+    size_t j = (size_t)tile * 32 + lane;
+    if (j >= out_size) continue;
+    const uint4* in = reinterpret_cast<const uint4*>(nodes + 8 * (in_size + 2 * j));
+    uint4 a = in[0], b = in[1], c = in[2], d = in[3];
+    uint32_t w[P2_RATE] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
+    uint4 o0, o1;
+    if (f64_role) {
+      double s[P2_CELLS];
+#pragma unroll
+      for (int i = 0; i < P2_RATE; i++) s[i] = p2f_from_mont(w[i]);
+#pragma unroll
+      for (int i = P2_RATE; i < P2_CELLS; i++) s[i] = 0.0;
+      p2f_permute(s, c_p2f);
+      o0 = make_uint4(p2f_to_mont(s[0]), p2f_to_mont(s[1]), p2f_to_mont(s[2]), p2f_to_mont(s[3]));
+      o1 = make_uint4(p2f_to_mont(s[4]), p2f_to_mont(s[5]), p2f_to_mont(s[6]), p2f_to_mont(s[7]));
+    } else {
+      uint32_t s[P2_CELLS];
+#pragma unroll
+      for (int i = 0; i < P2_RATE; i++) s[i] = w[i];
+#pragma unroll
+      for (int i = P2_RATE; i < P2_CELLS; i++) s[i] = 0u;
+      p2_permute_dev_compact(s, c_p2, ones);
+      o0 = make_uint4(s[0], s[1], s[2], s[3]);
+      o1 = make_uint4(s[4], s[5], s[6], s[7]);
+    }
+    uint4* o = reinterpret_cast<uint4*>(nodes + 8 * (out_size + j));
+    o[0] = o0;
+    o[1] = o1;
+  }
 }
 
 // Top of the tree in one launch: all layers from `start_out` parents down to the root are folded by a single CTA
@@ -213,7 +272,21 @@ b2z_err launch_hash_rows(b2z_ctx* ctx, uint32_t* out, const uint32_t* matrix, si
 b2z_err launch_hash_fold(b2z_ctx* ctx, uint32_t* nodes, size_t in_size, size_t out_size) {
   if (out_size == 0) return nullptr;
   B2Z_TRY(upload_consts(ctx));
-  hash_fold_kernel<<<(unsigned)((out_size + 127) / 128), 128, 0, ctx->stream>>>(nodes, in_size, out_size, 0xffffffffu);
+  const int mixed = env_int("B2Z_HASH_MIXED", 1);
+  const int ctas_per_sm = env_int("B2Z_HASH_CTAS", 6);
+  const int period = env_int("B2Z_HASH_ROLE_PERIOD", 2);
+  const int n_int = env_int("B2Z_HASH_ROLE_INT", 1);
+  const size_t grid = (size_t)ctx->sm_count * ctas_per_sm;
+  const size_t min_rows = (size_t)env_int("B2Z_HASH_MIXED_MIN_ROWS", (int)(grid * 128 * 4));
+  if (mixed && period >= 1 && out_size >= min_rows && out_size / 32 < 0xffffffffu) {
+    if (!ctx->hash_sched) B2Z_CUDA(cudaMalloc(&ctx->hash_sched, HASH_SCHED_WORDS * sizeof(unsigned)));
+    B2Z_CUDA(cudaMemsetAsync(ctx->hash_sched, 0, HASH_SCHED_WORDS * sizeof(unsigned), ctx->stream));
+    unsigned n_tiles = (unsigned)((out_size + 31) / 32);
+    auto kern = ctas_per_sm >= 8 ? hash_fold_mixed_kernel<8> : ctas_per_sm == 7 ? hash_fold_mixed_kernel<7> : hash_fold_mixed_kernel<6>;
+    kern<<<(unsigned)grid, 128, 0, ctx->stream>>>(nodes, in_size, out_size, 0xffffffffu, ctx->hash_sched, n_tiles, (unsigned)period, (unsigned)n_int);
+  } else {
+    hash_fold_kernel<<<(unsigned)((out_size + 127) / 128), 128, 0, ctx->stream>>>(nodes, in_size, out_size, 0xffffffffu);
+  }
   ctx->launches++;
   B2Z_CUDA(cudaGetLastError());
   return nullptr;
