@@ -70,6 +70,12 @@ b2z_err b2z_batch_bit_reverse(b2z_ctx* ctx, uint32_t* io, size_t count, unsigned
 b2z_err b2z_zk_shift(b2z_ctx* ctx, uint32_t* io, size_t count, unsigned po2);
 /* Hal::hash_rows(output, matrix): Poseidon2 sponge of every row of a column-major [cols][rows] matrix */
 b2z_err b2z_hash_rows(b2z_ctx* ctx, uint32_t* out_digests, const uint32_t* matrix, size_t rows, size_t cols);
+/* The same sponge absorbed in column chunks (b2z_prove_segment hashes each witness chunk as it lands over PCIe):
+ * call with the chunks of the matrix in order, carry_in = 0 on the first, last = 1 on the final one; every non-final
+ * chunk must be a positive multiple of 16 columns.  `out_digests` (8 words per row) holds the carried sponge capacity
+ * between calls and the digests after the last call -- identical to one b2z_hash_rows over all the columns. */
+b2z_err b2z_hash_rows_chunk(b2z_ctx* ctx, uint32_t* out_digests, const uint32_t* matrix_chunk, size_t rows, size_t cols, int carry_in,
+                            int last);
 /* Hal::hash_fold(io, input_size, output_size): node[out+j] = hash_pair(node[in+2j], node[in+2j+1]) */
 b2z_err b2z_hash_fold(b2z_ctx* ctx, uint32_t* nodes, size_t in_size, size_t out_size);
 /* MerkleTreeProver::new (prove/merkle.rs): hash_rows into nodes[rows..2rows) then every hash_fold layer */

@@ -296,3 +296,33 @@ def test_merkle_build_mixed_default_large(hal, oracle):
     hal.free(d)
     hal.free(nodes)
     assert np.array_equal(got[8:], want[8:])
+
+
+@pytest.mark.parametrize("mode", ["int_only", "mixed", "f64_only"])
+@pytest.mark.parametrize("rows,chunks", [(1 << 12, (16, 32, 8)), (1 << 12, (32, 32)), (96, (16, 1)), (1 << 13, (48,))])
+def test_hash_rows_chunk_carries_the_sponge(hal, oracle, monkeypatch, rows, chunks, mode):
+    """b2z_hash_rows_chunk over consecutive column chunks == one hash_rows over all the columns, whichever stream resumes a row."""
+    if mode == "int_only":
+        monkeypatch.setenv("B2Z_HASH_MIXED", "0")
+    else:
+        monkeypatch.setenv("B2Z_HASH_MIXED_MIN_ROWS", "0")
+        monkeypatch.setenv("B2Z_HASH_ROLE_PERIOD", "2" if mode == "mixed" else "1")
+        monkeypatch.setenv("B2Z_HASH_ROLE_INT", "1" if mode == "mixed" else "0")
+    cols = sum(chunks)
+    m = rand_fp(np.random.default_rng(rows + cols), rows * cols)
+    dm, do = hal.copy_from(m), hal.alloc(8 * rows)
+    c0 = 0
+    for k, c in enumerate(chunks):
+        hal.hash_rows_chunk(do, dm + 4 * c0 * rows, rows, c, carry_in=k > 0, last=k == len(chunks) - 1)
+        c0 += c
+    assert np.array_equal(hal.view(do, 8 * rows), oracle.hash_rows(m, rows, cols))
+    hal.free(dm)
+    hal.free(do)
+
+
+def test_hash_rows_chunk_rejects_ragged_middle_chunk(hal):
+    do, dm = hal.alloc(8 * 64), hal.alloc(64 * 20)
+    with pytest.raises(RuntimeError):
+        hal.hash_rows_chunk(do, dm, 64, 20, carry_in=False, last=False)
+    hal.free(do)
+    hal.free(dm)

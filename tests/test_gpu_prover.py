@@ -144,3 +144,38 @@ def test_baseline_size_segments_verify(hal, po2):
     for p in (dcode, ddata, dglob, dnoise):
         hal.free(p)
     c.close()
+
+
+def test_seal_parity_host_api_planning_circuit_chunked_leaves(hal, oracle):
+    """Host-buffer API on the W = 256 circuit: the data group arrives in 32-column chunks and its leaves are hashed chunk by
+    chunk (launch_hash_rows_chunk) -- the seal must still be the oracle's, word for word."""
+    sc = S.circuit_planning()
+    po2 = 12
+    oc, code, data, glob, noise, zk = _witness(oracle, sc, po2, 0xB2000003)
+    want = oc.prove(po2, code, data, glob, noise, zk)
+    c = H.Circuit(hal, sc.blob)
+    got = hal.prove_segment(c, po2, code, data, glob, noise, zk)
+    assert np.array_equal(got, want)
+    c.close()
+
+
+def test_host_and_device_api_agree_at_mixed_kernel_sizes(hal):
+    """po2 = 18 (2^20 leaves: the mixed INT / FP64 kernels run, with carried sponge state on the host path): the chunked
+    host-buffer API and the one-shot device API must produce the same seal from the same witness."""
+    sc = S.circuit_planning()
+    po2, zk = 18, 1994
+    n = 1 << po2
+    wa, wc, wd = sc.group_sizes
+    c = H.Circuit(hal, sc.blob)
+    dcode, ddata = hal.alloc(wc * n), hal.alloc(wd * n)
+    dglob, dnoise = hal.alloc(sc.globals_size), hal.alloc(wa * zk)
+    hal.witgen(c, po2, dcode, ddata, dglob, dnoise, 0xB2000004, zk)
+    glob = hal.view(dglob, sc.globals_size)
+    code, data, noise = hal.view(dcode, wc * n), hal.view(ddata, wd * n), hal.view(dnoise, wa * zk)
+    dev = hal.prove_segment_device(c, po2, dcode, ddata, glob, dnoise, zk)
+    host = hal.prove_segment(c, po2, code, data, glob, noise, zk)
+    assert np.array_equal(dev, host)
+    assert c.verify(host) == 0
+    for p in (dcode, ddata, dglob, dnoise):
+        hal.free(p)
+    c.close()

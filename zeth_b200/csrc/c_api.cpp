@@ -133,6 +133,10 @@ b2z_err b2z_hash_rows(b2z_ctx* ctx, uint32_t* out, const uint32_t* matrix, size_
   CTX_GUARD();
   return launch_hash_rows(ctx, out, matrix, rows, cols);
 }
+b2z_err b2z_hash_rows_chunk(b2z_ctx* ctx, uint32_t* out, const uint32_t* matrix, size_t rows, size_t cols, int carry_in, int last) {
+  CTX_GUARD();
+  return launch_hash_rows_chunk(ctx, out, matrix, rows, cols, carry_in != 0, last != 0);
+}
 b2z_err b2z_hash_fold(b2z_ctx* ctx, uint32_t* nodes, size_t in_size, size_t out_size) {
   CTX_GUARD();
   return launch_hash_fold(ctx, nodes, in_size, out_size);

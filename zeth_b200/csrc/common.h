@@ -65,6 +65,8 @@ b2z_err launch_evaluate(b2z_ctx* ctx, uint32_t* out, const uint32_t* in, size_t 
 b2z_err launch_bit_reverse(b2z_ctx* ctx, uint32_t* io, size_t count, unsigned po2);
 b2z_err launch_zk_shift(b2z_ctx* ctx, uint32_t* io, size_t count, unsigned po2);
 b2z_err launch_hash_rows(b2z_ctx* ctx, uint32_t* out, const uint32_t* matrix, size_t rows, size_t cols);
+// column-chunked leaf hashing: `out` (8 words per row) carries the sponge capacity between chunks, the digest after the last
+b2z_err launch_hash_rows_chunk(b2z_ctx* ctx, uint32_t* out, const uint32_t* matrix, size_t rows, size_t cols, bool carry_in, bool last);
 b2z_err launch_hash_fold(b2z_ctx* ctx, uint32_t* nodes, size_t in_size, size_t out_size);
 // all fold layers with <= start_out parents, one launch (node layout as hash_fold: in_size = 2 * out_size)
 b2z_err launch_hash_fold_top(b2z_ctx* ctx, uint32_t* nodes, size_t start_out);

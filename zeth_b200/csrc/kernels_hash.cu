@@ -30,14 +30,26 @@ static b2z_err upload_consts(b2z_ctx* ctx) {
   return nullptr;
 }
 
+// Column-chunked absorption (used when a witness is still arriving over PCIe, prover.cpp commit_group): a launch may
+// start from the capacity cells left by the previous chunk (HASH_CARRY_IN) and may stop before squeezing (no HASH_LAST).
+// The 8 carried words of a row live in that row's digest slot, as canonical Montgomery words, so either stream can
+// resume a row the other one started.  In overwrite mode the rate cells never need saving.  Non-final chunks must be
+// whole blocks (cols % 16 == 0, cols > 0).
+constexpr unsigned HASH_CARRY_IN = 1, HASH_LAST = 2;
+
 template <int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) hash_rows_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ matrix, size_t rows,
-                                                                  size_t cols, uint32_t ones) {
+                                                                  size_t cols, uint32_t ones, unsigned flags) {
   size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (r >= rows) return;
   uint32_t s[P2_CELLS];
 #pragma unroll
   for (int i = 0; i < P2_CELLS; i++) s[i] = 0;
+  uint4* o = reinterpret_cast<uint4*>(out + 8 * r);
+  if (flags & HASH_CARRY_IN) {
+    uint4 a = o[0], b = o[1];
+    s[16] = a.x, s[17] = a.y, s[18] = a.z, s[19] = a.w, s[20] = b.x, s[21] = b.y, s[22] = b.z, s[23] = b.w;
+  }
   const uint32_t* p = matrix + r;
   size_t full = cols / P2_RATE;
   for (size_t blk = 0; blk < full; blk++) {
@@ -46,14 +58,18 @@ __global__ void __launch_bounds__(THREADS, MINB) hash_rows_kernel(uint32_t* __re
     p2_permute_dev(s, c_p2, ones);
   }
   size_t rem = cols - full * P2_RATE;
-  if (rem != 0 || cols == 0) {
+  if (rem != 0 || (cols == 0 && !(flags & HASH_CARRY_IN))) {
 #pragma unroll
     for (int i = 0; i < P2_RATE; i++) s[i] = (size_t)i < rem ? __ldg(p + (full * P2_RATE + i) * rows) : 0u;
     p2_permute_dev(s, c_p2, ones);
   }
-  uint4* o = reinterpret_cast<uint4*>(out + 8 * r);
-  o[0] = make_uint4(s[0], s[1], s[2], s[3]);
-  o[1] = make_uint4(s[4], s[5], s[6], s[7]);
+  if (flags & HASH_LAST) {
+    o[0] = make_uint4(s[0], s[1], s[2], s[3]);
+    o[1] = make_uint4(s[4], s[5], s[6], s[7]);
+  } else {
+    o[0] = make_uint4(s[16], s[17], s[18], s[19]);
+    o[1] = make_uint4(s[20], s[21], s[22], s[23]);
+  }
 }
 
 // ---- mixed INT / FP64 leaf hashing ----
@@ -81,12 +97,17 @@ __device__ __forceinline__ uint32_t ld_col_guarded(const uint32_t* p, unsigned i
   return v;
 }
 __device__ __forceinline__ void hash_row_int(uint32_t* __restrict__ out, const uint32_t* __restrict__ matrix, size_t rows, size_t cols, size_t r,
-                                             uint32_t ones) {
+                                             uint32_t ones, unsigned flags) {
   uint32_t s[P2_CELLS];
 #pragma unroll
   for (int i = 0; i < P2_CELLS; i++) s[i] = 0;
+  uint4* o = reinterpret_cast<uint4*>(out + 8 * r);
+  if (flags & HASH_CARRY_IN) {
+    uint4 a = o[0], b = o[1];
+    s[16] = a.x, s[17] = a.y, s[18] = a.z, s[19] = a.w, s[20] = b.x, s[21] = b.y, s[22] = b.z, s[23] = b.w;
+  }
   const uint32_t* p = matrix + r;
-  const size_t nblk = cols == 0 ? 1 : (cols + P2_RATE - 1) / P2_RATE;
+  const size_t nblk = (cols == 0 && !(flags & HASH_CARRY_IN)) ? 1 : (cols + P2_RATE - 1) / P2_RATE;
 #pragma unroll 1
   for (size_t blk = 0; blk < nblk; blk++) {
     const unsigned left = (unsigned)min(cols - blk * P2_RATE, (size_t)P2_RATE);  // columns in this block (0 only when cols == 0)
@@ -97,17 +118,28 @@ __device__ __forceinline__ void hash_row_int(uint32_t* __restrict__ out, const u
     }
     p2_permute_dev_compact(s, c_p2, ones);
   }
-  uint4* o = reinterpret_cast<uint4*>(out + 8 * r);
-  o[0] = make_uint4(s[0], s[1], s[2], s[3]);
-  o[1] = make_uint4(s[4], s[5], s[6], s[7]);
+  const int base = (flags & HASH_LAST) ? 0 : P2_RATE;  // squeeze the digest, or park the capacity cells
+  uint32_t w[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) w[i] = base ? s[P2_RATE + i] : s[i];
+  o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+  o[1] = make_uint4(w[4], w[5], w[6], w[7]);
 }
 
-__device__ __forceinline__ void hash_row_f64(uint32_t* __restrict__ out, const uint32_t* __restrict__ matrix, size_t rows, size_t cols, size_t r) {
+__device__ __forceinline__ void hash_row_f64(uint32_t* __restrict__ out, const uint32_t* __restrict__ matrix, size_t rows, size_t cols, size_t r,
+                                             unsigned flags) {
   double s[P2_CELLS];
 #pragma unroll
   for (int i = 0; i < P2_CELLS; i++) s[i] = 0.0;
+  uint4* o = reinterpret_cast<uint4*>(out + 8 * r);
+  if (flags & HASH_CARRY_IN) {
+    uint4 a = o[0], b = o[1];
+    uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int i = 0; i < 8; i++) s[P2_RATE + i] = p2f_from_mont(w[i]);
+  }
   const uint32_t* p = matrix + r;
-  const size_t nblk = cols == 0 ? 1 : (cols + P2_RATE - 1) / P2_RATE;
+  const size_t nblk = (cols == 0 && !(flags & HASH_CARRY_IN)) ? 1 : (cols + P2_RATE - 1) / P2_RATE;
 #pragma unroll 1
   for (size_t blk = 0; blk < nblk; blk++) {
     const unsigned left = (unsigned)min(cols - blk * P2_RATE, (size_t)P2_RATE);
@@ -120,15 +152,18 @@ __device__ __forceinline__ void hash_row_f64(uint32_t* __restrict__ out, const u
     for (int i = P2_RATE; i < P2_CELLS; i++) s[i] = p2f_reduce(s[i]);  // carried capacity cells back below 2^31
     p2f_permute(s, c_p2f);
   }
-  uint4* o = reinterpret_cast<uint4*>(out + 8 * r);
-  o[0] = make_uint4(p2f_to_mont(s[0]), p2f_to_mont(s[1]), p2f_to_mont(s[2]), p2f_to_mont(s[3]));
-  o[1] = make_uint4(p2f_to_mont(s[4]), p2f_to_mont(s[5]), p2f_to_mont(s[6]), p2f_to_mont(s[7]));
+  const int base = (flags & HASH_LAST) ? 0 : P2_RATE;
+  uint32_t w[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) w[i] = p2f_to_mont(base ? s[P2_RATE + i] : s[i]);
+  o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+  o[1] = make_uint4(w[4], w[5], w[6], w[7]);
 }
 
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) hash_rows_mixed_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ matrix, size_t rows,
                                                                     size_t cols, uint32_t ones, unsigned* __restrict__ sched, unsigned n_tiles,
-                                                                    unsigned period, unsigned n_int) {
+                                                                    unsigned period, unsigned n_int, unsigned flags) {
   __shared__ unsigned s_role;
   if (threadIdx.x == 0) {
     unsigned smid;
@@ -145,8 +180,8 @@ __global__ void __launch_bounds__(128, MINB) hash_rows_mixed_kernel(uint32_t* __
     if (tile >= n_tiles) break;
     size_t r = (size_t)tile * 32 + lane;
     if (r < rows) {
-      if (f64_role) hash_row_f64(out, matrix, rows, cols, r);
-      else hash_row_int(out, matrix, rows, cols, r, ones);
+      if (f64_role) hash_row_f64(out, matrix, rows, cols, r, flags);
+      else hash_row_int(out, matrix, rows, cols, r, ones, flags);
     }
   }
 }
@@ -244,7 +279,13 @@ static int env_int(const char* name, int dflt) {
 }
 
 b2z_err launch_hash_rows(b2z_ctx* ctx, uint32_t* out, const uint32_t* matrix, size_t rows, size_t cols) {
+  return launch_hash_rows_chunk(ctx, out, matrix, rows, cols, false, true);
+}
+
+b2z_err launch_hash_rows_chunk(b2z_ctx* ctx, uint32_t* out, const uint32_t* matrix, size_t rows, size_t cols, bool carry_in, bool last) {
   if (rows == 0) return nullptr;
+  B2Z_REQUIRE(last || (cols > 0 && cols % P2_RATE == 0), "hash_rows_chunk: a non-final chunk must be a positive multiple of 16 columns");
+  const unsigned flags = (carry_in ? HASH_CARRY_IN : 0u) | (last ? HASH_LAST : 0u);
   B2Z_TRY(upload_consts(ctx));
   // B2Z_HASH_MIXED=0 forces the INT-only kernel; the mixed kernel needs enough rows to fill the persistent grid
   // (read per call so that tests and sweeps can switch modes inside one process)
@@ -260,9 +301,9 @@ b2z_err launch_hash_rows(b2z_ctx* ctx, uint32_t* out, const uint32_t* matrix, si
     unsigned n_tiles = (unsigned)((rows + 31) / 32);
     auto kern = ctas_per_sm >= 8 ? hash_rows_mixed_kernel<8> : ctas_per_sm == 7 ? hash_rows_mixed_kernel<7> : hash_rows_mixed_kernel<6>;
     kern<<<(unsigned)grid, 128, 0, ctx->stream>>>(out, matrix, rows, cols, 0xffffffffu, ctx->hash_sched, n_tiles, (unsigned)period,
-                                                  (unsigned)n_int);
+                                                  (unsigned)n_int, flags);
   } else {
-    hash_rows_kernel<128, 1><<<(unsigned)((rows + 127) / 128), 128, 0, ctx->stream>>>(out, matrix, rows, cols, 0xffffffffu);
+    hash_rows_kernel<128, 1><<<(unsigned)((rows + 127) / 128), 128, 0, ctx->stream>>>(out, matrix, rows, cols, 0xffffffffu, flags);
   }
   ctx->launches++;
   B2Z_CUDA(cudaGetLastError());

@@ -90,8 +90,8 @@ struct MerkleParams {
   size_t path_words() const { return 8 * (layers - ilog2(top_size)); }
 };
 
-b2z_err merkle_build(b2z_ctx* ctx, uint32_t* nodes, const uint32_t* matrix, size_t rows, size_t cols) {
-  B2Z_TRY(launch_hash_rows(ctx, nodes + 8 * rows, matrix, rows, cols));
+// interior layers over leaves already sitting in nodes[rows .. 2 rows)
+static b2z_err merkle_fold_layers(b2z_ctx* ctx, uint32_t* nodes, size_t rows) {
   // wide layers: one launch each; the top of the tree (<= 512 parents per layer) in a single launch
   constexpr size_t TOP = 512;
   size_t i = ilog2(rows);
@@ -104,6 +104,11 @@ b2z_err merkle_build(b2z_ctx* ctx, uint32_t* nodes, const uint32_t* matrix, size
     B2Z_TRY(launch_hash_fold(ctx, nodes, 2 * out, out));
   }
   return nullptr;
+}
+
+b2z_err merkle_build(b2z_ctx* ctx, uint32_t* nodes, const uint32_t* matrix, size_t rows, size_t cols) {
+  B2Z_TRY(launch_hash_rows(ctx, nodes + 8 * rows, matrix, rows, cols));
+  return merkle_fold_layers(ctx, nodes, rows);
 }
 
 struct PolyGroupDev {
@@ -129,7 +134,7 @@ static b2z_err ensure_pinned(b2z_ctx* ctx, size_t words) {
 struct PolyGroupDev;
 struct Seal;
 // PolyGroup::new + merkle.commit: coeffs (bit-reversed, shifted) -> LDE, natural-order coeffs, Merkle tree, top layer + root
-static b2z_err poly_group_finish(b2z_ctx* ctx, DevMem& mem, PolyGroupDev& pg, unsigned po2, Seal& seal, HostRng& rng);
+static b2z_err poly_group_finish(b2z_ctx* ctx, DevMem& mem, PolyGroupDev& pg, unsigned po2, Seal& seal, HostRng& rng, bool leaves_done = false);
 static b2z_err poly_group_commit(b2z_ctx* ctx, DevMem& mem, PolyGroupDev& pg, uint32_t* coeffs, size_t count, unsigned po2, Seal& seal,
                                  HostRng& rng) {
   size_t n = (size_t)1 << po2, domain = 4 * n;
@@ -141,13 +146,18 @@ static b2z_err poly_group_commit(b2z_ctx* ctx, DevMem& mem, PolyGroupDev& pg, ui
   return poly_group_finish(ctx, mem, pg, po2, seal, rng);
 }
 // natural-order coefficients, Merkle tree over the LDE, top layer -> seal, root -> transcript
-static b2z_err poly_group_finish(b2z_ctx* ctx, DevMem& mem, PolyGroupDev& pg, unsigned po2, Seal& seal, HostRng& rng) {
+// (`leaves_done`: the caller already hashed the leaves chunk by chunk into pg.nodes)
+static b2z_err poly_group_finish(b2z_ctx* ctx, DevMem& mem, PolyGroupDev& pg, unsigned po2, Seal& seal, HostRng& rng, bool leaves_done) {
   size_t n = (size_t)1 << po2, domain = 4 * n;
   size_t count = pg.count;
   uint32_t* coeffs = pg.coeffs;
   B2Z_TRY(launch_bit_reverse(ctx, coeffs, count, po2));
-  B2Z_TRY(mem.alloc(&pg.nodes, 2 * domain * 8));
-  B2Z_TRY(merkle_build(ctx, pg.nodes, pg.evaluated, domain, count));
+  if (leaves_done) {
+    B2Z_TRY(merkle_fold_layers(ctx, pg.nodes, domain));
+  } else {
+    B2Z_TRY(mem.alloc(&pg.nodes, 2 * domain * 8));
+    B2Z_TRY(merkle_build(ctx, pg.nodes, pg.evaluated, domain, count));
+  }
   MerkleParams mp(domain, count);
   B2Z_REQUIRE(seal.pos + 8 * mp.top_size <= seal.cap, "seal overflow");
   B2Z_CUDA(cudaMemcpyAsync(seal.w + seal.pos, pg.nodes + 8 * mp.top_size, 32 * mp.top_size, cudaMemcpyDeviceToHost, ctx->stream));
@@ -160,7 +170,9 @@ static b2z_err poly_group_finish(b2z_ctx* ctx, DevMem& mem, PolyGroupDev& pg, un
 }
 
 // Optional readiness of a host-uploaded witness: the upload runs on ctx->copy_stream in column chunks, the commit
-// consumes each chunk as soon as its event fires (upload of chunk k+1 overlaps the iNTT / LDE of chunk k).
+// consumes each chunk as soon as its event fires: iNTT, LDE and -- when the chunk is a whole number of sponge blocks --
+// the leaf hashing of its columns (launch_hash_rows_chunk carries the sponge capacity in the leaf slots), so the
+// upload of chunk k+1 hides behind all the work on chunk k and only the interior Merkle layers remain at the end.
 struct WitnessReady {
   cudaEvent_t code = nullptr, noise = nullptr;
   std::vector<cudaEvent_t> data_chunks;  // one event per `chunk_cols` data columns
@@ -180,14 +192,19 @@ static b2z_err commit_group(b2z_ctx* ctx, DevMem& mem, PolyGroupDev& pg, const u
   B2Z_TRY(mem.alloc(&pg.evaluated, count * domain));
   if (whole_event) B2Z_CUDA(cudaStreamWaitEvent(ctx->stream, whole_event, 0));
   if (!chunk_events || chunk_cols == 0) chunk_cols = count;
+  const bool hash_chunks = chunk_cols < count && chunk_cols % 16 == 0;
+  if (hash_chunks) B2Z_TRY(mem.alloc(&pg.nodes, 2 * domain * 8));
   for (size_t c0 = 0, k = 0; c0 < count; c0 += chunk_cols, k++) {
     size_t cols = count - c0 < chunk_cols ? count - c0 : chunk_cols;
     if (chunk_events && k < chunk_events->size()) B2Z_CUDA(cudaStreamWaitEvent(ctx->stream, (*chunk_events)[k], 0));
     // the first inverse pass reads the witness directly and writes the coefficient buffer (no separate copy)
     B2Z_TRY(launch_interpolate(ctx, coeffs + c0 * n, cols, po2, /*fuse_zk_shift=*/true, witness + c0 * n));
     B2Z_TRY(launch_evaluate(ctx, pg.evaluated + c0 * domain, coeffs + c0 * n, cols, po2 + 2, 2));
+    if (hash_chunks)
+      B2Z_TRY(launch_hash_rows_chunk(ctx, pg.nodes + 8 * domain, pg.evaluated + c0 * domain, domain, cols, /*carry_in=*/c0 != 0,
+                                     /*last=*/c0 + cols == count));
   }
-  return poly_group_finish(ctx, mem, pg, po2, seal, rng);
+  return poly_group_finish(ctx, mem, pg, po2, seal, rng, hash_chunks);
 }
 
 // unique interpolant through (x_i, fx_i) -> monomial coefficients (core/poly.rs poly_interpolate)

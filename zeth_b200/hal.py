@@ -30,7 +30,7 @@ def lib_path() -> str:
 _ERR_FUNCS = [
     "b2z_init", "b2z_destroy", "b2z_set_stream", "b2z_sync", "b2z_alloc", "b2z_free", "b2z_h2d", "b2z_d2h",
     "b2z_batch_interpolate_ntt", "b2z_batch_evaluate_ntt", "b2z_batch_expand_into_evaluate_ntt", "b2z_batch_bit_reverse",
-    "b2z_zk_shift", "b2z_hash_rows", "b2z_hash_fold", "b2z_merkle_build", "b2z_fri_fold", "b2z_batch_evaluate_any",
+    "b2z_zk_shift", "b2z_hash_rows", "b2z_hash_rows_chunk", "b2z_hash_fold", "b2z_merkle_build", "b2z_fri_fold", "b2z_batch_evaluate_any",
     "b2z_mix_poly_coeffs", "b2z_eltwise_add_elem", "b2z_eltwise_sum_extelem", "b2z_eltwise_copy_elem",
     "b2z_eltwise_zeroize_elem", "b2z_gather_sample", "b2z_poly_divide", "b2z_circuit_load", "b2z_circuit_precompile",
     "b2z_circuit_free", "b2z_eval_check", "b2z_accumulate", "b2z_witgen", "b2z_prove_segment_device", "b2z_prove_segment",
@@ -182,6 +182,10 @@ class Hal:
 
     def hash_rows(self, out: int, matrix: int, rows: int, cols: int):
         _chk(self.L.b2z_hash_rows(self.ctx, C.c_void_p(out), C.c_void_p(matrix), C.c_size_t(rows), C.c_size_t(cols)))
+
+    def hash_rows_chunk(self, out: int, matrix_chunk: int, rows: int, cols: int, carry_in: bool, last: bool):
+        _chk(self.L.b2z_hash_rows_chunk(self.ctx, C.c_void_p(out), C.c_void_p(matrix_chunk), C.c_size_t(rows), C.c_size_t(cols),
+                                        C.c_int(int(carry_in)), C.c_int(int(last))))
 
     def hash_fold(self, nodes: int, in_size: int, out_size: int):
         _chk(self.L.b2z_hash_fold(self.ctx, C.c_void_p(nodes), C.c_size_t(in_size), C.c_size_t(out_size)))
