@@ -174,9 +174,10 @@ static b2z_err poly_group_finish(b2z_ctx* ctx, DevMem& mem, PolyGroupDev& pg, un
 // the leaf hashing of its columns (launch_hash_rows_chunk carries the sponge capacity in the leaf slots), so the
 // upload of chunk k+1 hides behind all the work on chunk k and only the interior Merkle layers remain at the end.
 struct WitnessReady {
-  cudaEvent_t code = nullptr, noise = nullptr;
+  cudaEvent_t noise = nullptr;
+  std::vector<cudaEvent_t> code_chunks;  // one event per `code_chunk_cols` code columns (small: the first compute starts early)
   std::vector<cudaEvent_t> data_chunks;  // one event per `chunk_cols` data columns
-  size_t chunk_cols = 0;
+  size_t chunk_cols = 0, code_chunk_cols = 0;
 };
 
 // prover.rs make_coeffs + commit_group (PolyGroup::new inlined so that the per-chunk work can start early)
@@ -271,7 +272,8 @@ b2z_err prove_segment_device(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, c
 
   PolyGroupDev pg[3], check_pg;
   tm.begin(0);
-  B2Z_TRY(commit_group(ctx, mem, pg[B2Z_GROUP_CODE], code_dev, wc, po2, seal, rng, nullptr, 0, ready ? ready->code : nullptr));
+  B2Z_TRY(commit_group(ctx, mem, pg[B2Z_GROUP_CODE], code_dev, wc, po2, seal, rng, ready ? &ready->code_chunks : nullptr,
+                       ready ? ready->code_chunk_cols : 0));
   tm.end(0);
   tm.begin(1);
   B2Z_TRY(commit_group(ctx, mem, pg[B2Z_GROUP_DATA], data_dev, wd, po2, seal, rng, ready ? &ready->data_chunks : nullptr,
@@ -528,8 +530,10 @@ b2z_err prove_segment_host(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, con
   if (!ctx->copy_stream) B2Z_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   WitnessReady ready;
   ready.chunk_cols = 32;
+  ready.code_chunk_cols = 4;  // the very first transfer is the only one nothing can hide: keep it short
   size_t nchunks = (wd + ready.chunk_cols - 1) / ready.chunk_cols;
-  while (ctx->h2d_events.size() < nchunks + 3) {
+  size_t ncode = (wc + ready.code_chunk_cols - 1) / ready.code_chunk_cols;
+  while (ctx->h2d_events.size() < nchunks + ncode + 2) {
     cudaEvent_t e;
     B2Z_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     ctx->h2d_events.push_back(e);
@@ -539,12 +543,15 @@ b2z_err prove_segment_host(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, con
   B2Z_CUDA(cudaMallocAsync(&data, 4 * (wd * n + 1), ctx->stream));
   B2Z_CUDA(cudaMallocAsync(&noise, 4 * (wa * zk_rows + 1), ctx->stream));
   // the copy stream may only touch the buffers once the (stream-ordered) allocations are visible
-  cudaEvent_t alloc_done = ctx->h2d_events[nchunks + 2];
+  cudaEvent_t alloc_done = ctx->h2d_events[nchunks + ncode + 1];
   B2Z_CUDA(cudaEventRecord(alloc_done, ctx->stream));
   B2Z_CUDA(cudaStreamWaitEvent(ctx->copy_stream, alloc_done, 0));
-  B2Z_CUDA(cudaMemcpyAsync(code, code_host, 4 * wc * n, cudaMemcpyHostToDevice, ctx->copy_stream));
-  ready.code = ctx->h2d_events[nchunks];
-  B2Z_CUDA(cudaEventRecord(ready.code, ctx->copy_stream));
+  for (size_t k = 0; k < ncode; k++) {
+    size_t c0 = k * ready.code_chunk_cols, cols = wc - c0 < ready.code_chunk_cols ? wc - c0 : ready.code_chunk_cols;
+    B2Z_CUDA(cudaMemcpyAsync(code + c0 * n, code_host + c0 * n, 4 * cols * n, cudaMemcpyHostToDevice, ctx->copy_stream));
+    B2Z_CUDA(cudaEventRecord(ctx->h2d_events[nchunks + k], ctx->copy_stream));
+    ready.code_chunks.push_back(ctx->h2d_events[nchunks + k]);
+  }
   for (size_t k = 0; k < nchunks; k++) {
     size_t c0 = k * ready.chunk_cols, cols = wd - c0 < ready.chunk_cols ? wd - c0 : ready.chunk_cols;
     B2Z_CUDA(cudaMemcpyAsync(data + c0 * n, data_host + c0 * n, 4 * cols * n, cudaMemcpyHostToDevice, ctx->copy_stream));
@@ -552,7 +559,7 @@ b2z_err prove_segment_host(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, con
     ready.data_chunks.push_back(ctx->h2d_events[k]);
   }
   B2Z_CUDA(cudaMemcpyAsync(noise, accum_noise_host, 4 * wa * zk_rows, cudaMemcpyHostToDevice, ctx->copy_stream));
-  ready.noise = ctx->h2d_events[nchunks + 1];
+  ready.noise = ctx->h2d_events[nchunks + ncode];
   B2Z_CUDA(cudaEventRecord(ready.noise, ctx->copy_stream));
   b2z_err err = prove_segment_device(ctx, c, po2, code, data, globals_host, noise, zk_rows, seal_host, seal_words, &ready);
   cudaStreamSynchronize(ctx->copy_stream);
