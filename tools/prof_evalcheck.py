@@ -23,4 +23,5 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 e0.record(stream)
 for _ in range(3): f()
 e1.record(stream); torch.cuda.synchronize()
-print(f"eval_check po2={po2} minblocks={os.environ.get('B2Z_EVALCHECK_MINBLOCKS','4')}: {e0.elapsed_time(e1)/3:.3f} ms")
+print(f"eval_check po2={po2} points_per_thread={os.environ.get('B2Z_EVALCHECK_POINTS','1')} "
+      f"minblocks={os.environ.get('B2Z_EVALCHECK_MINBLOCKS','default')}: {e0.elapsed_time(e1)/3:.3f} ms")

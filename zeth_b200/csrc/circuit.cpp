@@ -423,6 +423,14 @@ void circuit_codegen(b2z_circuit* c) {
   int parts_m = 120;
   if (const char* e = getenv("B2Z_EVALCHECK_PARTS")) parts_m = atoi(e);
   c->parts_mode = parts_m > 0;
+  // B2Z_EVALCHECK_POINTS = K > 1 (parts mode only): every thread evaluates K coset points and calls each part K times in
+  // a row, so a part's instructions are fetched once per K points.  The straight-line program is far larger than the
+  // instruction cache (planning circuit: ~190 KB of SASS, ncu: 49.5 % i-cache hits, "no instruction" the top stall);
+  // only the accumulator (4..8 words per point) is live across parts, so K points cost K x 8 registers.
+  int points_k = 1;
+  if (const char* e = getenv("B2Z_EVALCHECK_POINTS")) points_k = atoi(e);
+  if (points_k < 1 || points_k > 8 || parts_m <= 0) points_k = 1;
+  c->points_per_thread = (unsigned)points_k;
   const std::string cpn = parts_m > 0 ? "ccp" : "cp", kcn = parts_m > 0 ? "ckc" : "kc";
   std::ostringstream body;  // straight-line mode: kernel body text
   std::vector<Emitter::Stmt> stmts;
@@ -521,11 +529,56 @@ void circuit_codegen(b2z_circuit* c) {
       main_body << ");\n";
       for (size_t j = 0; j < outs.size(); j++) main_body << "  const u32 t" << outs[j] << " = r" << p << ".v[" << j << "];\n";
     }
-    o << "extern \"C\" __global__ void __launch_bounds__(128, " << min_blocks << ") b2z_eval_check(" << kernel_head_params << ") {\n";
-    o << "  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;\n  if (i > mask) return;\n  const u64 domain = mask + 1;\n";
-    for (unsigned b = 0; b <= max_back; b++) o << "  const u32 ib" << b << " = (u32)((i - " << 4 * b << "ull) & mask) << 2;\n";
-    o << main_body.str();
-    emit_tail(o);
+    if (points_k == 1) {
+      o << "extern \"C\" __global__ void __launch_bounds__(128, " << min_blocks << ") b2z_eval_check(" << kernel_head_params << ") {\n";
+      o << "  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;\n  if (i > mask) return;\n  const u64 domain = mask + 1;\n";
+      for (unsigned b = 0; b <= max_back; b++) o << "  const u32 ib" << b << " = (u32)((i - " << 4 * b << "ull) & mask) << 2;\n";
+      o << main_body.str();
+      emit_tail(o);
+    } else {
+      // K points per thread: point k of a thread is (blockIdx.x * K + k) * 128 + threadIdx.x (every k-slice is coalesced);
+      // names get a _<k> suffix, part p is called for k = 0..K-1 before part p + 1 starts
+      const int reg_blocks = std::max(1, 65536 / (128 * (48 + 12 * points_k)));
+      o << "extern \"C\" __global__ void __launch_bounds__(128, " << std::min(min_blocks, reg_blocks) << ") b2z_eval_check("
+        << kernel_head_params << ") {\n";
+      o << "  const u64 domain = mask + 1;\n";
+      for (int k = 0; k < points_k; k++) {
+        o << "  const u64 i_" << k << " = (((u64)blockIdx.x * " << points_k << " + " << k << ") * blockDim.x + threadIdx.x);\n";
+        for (unsigned b = 0; b <= max_back; b++)
+          o << "  const u32 ib" << b << "_" << k << " = (u32)((i_" << k << " - " << 4 * b << "ull) & mask) << 2;\n";
+      }
+      for (size_t p = 0; p + 1 < bounds.size(); p++) {
+        // recompute this part's ins / outs (same rule as above)
+        std::vector<unsigned> ins, outs;
+        std::map<unsigned, bool> seen;
+        for (size_t q = bounds[p]; q < bounds[p + 1]; q++) {
+          for (unsigned u : stmts[q].uses)
+            if (def_part[u] < p && !seen[u]) {
+              seen[u] = true;
+              ins.push_back(u);
+            }
+          if (last_use_part.count(stmts[q].id) && last_use_part[stmts[q].id] > p) outs.push_back(stmts[q].id);
+        }
+        for (int k = 0; k < points_k; k++) {
+          o << "  const PR" << p << " r" << p << "_" << k << " = part" << p << "(";
+          for (unsigned b = 0; b <= max_back; b++) o << (b ? ", ib" : "ib") << b << "_" << k;
+          for (unsigned u : ins) o << ", t" << u << "_" << k;
+          o << ");\n";
+          for (size_t j = 0; j < outs.size(); j++) o << "  const u32 t" << outs[j] << "_" << k << " = r" << p << "_" << k << ".v[" << j << "];\n";
+        }
+      }
+      for (int k = 0; k < points_k; k++) {
+        o << "  if (i_" << k << " <= mask) {\n";
+        o << "    const u32 iz = (i_" << k << " & 2) ? ((i_" << k << " & 1) ? iz3 : iz2) : ((i_" << k << " & 1) ? iz1 : iz0);\n";
+        for (int j = 0; j < 4; j++) {
+          std::string v = "0u";
+          if (result.ext || j == 0) v = result.c[j].tid >= 0 ? "t" + std::to_string(result.c[j].tid) + "_" + std::to_string(k) : result.c[j].str();
+          o << "    check[" << j << " * domain + i_" << k << "] = fmul(" << v << ", iz);\n";
+        }
+        o << "  }\n";
+      }
+      o << "}\n\n";
+    }
   }
   // ---- witgen: one thread per active trace row; taps read the trace domain (stride 1) ----
   o << "extern \"C\" __global__ void __launch_bounds__(256) b2z_witgen(const __grid_constant__ ColPtrs cp, "

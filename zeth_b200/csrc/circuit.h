@@ -30,6 +30,7 @@ struct b2z_circuit {
   cudaLibrary_t library = nullptr;
   cudaKernel_t k_eval_check = nullptr, k_witgen = nullptr;
   bool parts_mode = false;                    // eval_check split into __noinline__ parts; tables in module constants
+  unsigned points_per_thread = 1;             // coset points per thread of the generated eval_check (parts mode, B2Z_EVALCHECK_POINTS)
   void *ccp_dev = nullptr, *ckc_dev = nullptr;  // device addresses of the module's __constant__ tables (parts mode)
   // device-resident tables
   int device = -1;
