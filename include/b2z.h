@@ -9,11 +9,15 @@
  * (risc0-zkp 3.0.2 `hal/mod.rs` trait Hal, `prove/*.rs`; risc0-circuit-rv32im 4.0.2 CircuitHal), which is what a
  * Rust `impl Hal for B200Hal` shim binds.
  *
- * Conventions (same as upstream's FFI): every function returns NULL on success or a static/thread-local,
- * NUL-terminated error string (do not free).  Field elements are u32 Montgomery words < P = 15*2^27+1; matrices
+ * Conventions (same as upstream's FFI): every function returns NULL on success or a NUL-terminated error string.
+ * OWNERSHIP DIFFERENCE from upstream: risc0-sys returns a heap string that the Rust side copies and frees; here the
+ * string is owned by the library (thread-local, valid until the same thread's next failing call) -- the caller copies it
+ * and must NOT free it (INTEGRATION.md shows the Rust `CStr::from_ptr(..).to_owned()` side).  Field elements are u32 Montgomery words < P = 15*2^27+1; matrices
  * are column-major [cols][rows]; ext elements are 4 consecutive words; digests are 8 words.  All `dev` pointers
  * are device pointers of the context's device; work is enqueued on the context's stream and is asynchronous
- * unless stated.  A context is single-threaded (upstream `Rc<dyn Prover>` is !Send): one context per thread.
+ * unless stated.  A context is single-threaded (upstream `Rc<dyn Prover>` is !Send): one context per thread; it may be
+ * created on one thread and used on another (zeth builds the prover inside spawn_blocking, lib.rs:131): every entry
+ * point re-asserts the context's device on the calling thread.
  * There is NO CPU fallback: without a usable CUDA device every compute entry point returns an error.
  */
 #ifndef B2Z_H
@@ -27,20 +31,22 @@ extern "C" {
 
 typedef struct b2z_ctx b2z_ctx;
 typedef struct b2z_circuit b2z_circuit;
+typedef struct b2z_session b2z_session;
 typedef const char* b2z_err;
 
-/* protocol constants (risc0-zkp 3.0.2 src/lib.rs) */
-#define B2Z_INV_RATE 4
-#define B2Z_QUERIES 50
-#define B2Z_FRI_FOLD 16
-#define B2Z_FRI_MIN_DEGREE 256
-#define B2Z_EXT_SIZE 4
-#define B2Z_CHECK_SIZE 16
-#define B2Z_DIGEST_WORDS 8
-#define B2Z_ZK_CYCLES 1994
-#define B2Z_GROUP_ACCUM 0
-#define B2Z_GROUP_CODE 1
-#define B2Z_GROUP_DATA 2
+/* protocol constants (risc0-zkp 3.0.2 src/lib.rs): single source of truth with confidence tags in protocol_params.h */
+#include "protocol_params.h"
+#define B2Z_INV_RATE PP_INV_RATE
+#define B2Z_QUERIES PP_QUERIES
+#define B2Z_FRI_FOLD PP_FRI_FOLD
+#define B2Z_FRI_MIN_DEGREE PP_FRI_MIN_DEGREE
+#define B2Z_EXT_SIZE PP_EXT_SIZE
+#define B2Z_CHECK_SIZE PP_CHECK_SIZE
+#define B2Z_DIGEST_WORDS PP_DIGEST_WORDS
+#define B2Z_ZK_CYCLES PP_ZK_CYCLES
+#define B2Z_GROUP_ACCUM PP_GROUP_ACCUM
+#define B2Z_GROUP_CODE PP_GROUP_CODE
+#define B2Z_GROUP_DATA PP_GROUP_DATA
 
 /* ---- context / memory: replaces CudaHal::new + Buffer alloc / copy_from / view (hal/cuda.rs) ---- */
 const char* b2z_version(void);
@@ -95,6 +101,11 @@ b2z_err b2z_eltwise_copy_elem(b2z_ctx* ctx, uint32_t* out, const uint32_t* in, s
 b2z_err b2z_eltwise_zeroize_elem(b2z_ctx* ctx, uint32_t* io, size_t n);
 /* Hal::gather_sample(dst, src, idx, size, stride) */
 b2z_err b2z_gather_sample(b2z_ctx* ctx, uint32_t* dst, const uint32_t* src, size_t idx, size_t size, size_t stride);
+/* Hal::scatter(into, index, offsets, values): CSR form -- `index` holds count + 1 starts; cycle c performs
+ * into[offsets[i]] = values[i] for i in [index[c], index[c+1]) in order.  All four are device arrays. */
+b2z_err b2z_scatter(b2z_ctx* ctx, uint32_t* into, const uint32_t* index, const uint32_t* offsets, const uint32_t* values, size_t count);
+/* Hal::prefix_products(io): in-place inclusive prefix product of `n` AoS ext elements (4 words each) */
+b2z_err b2z_prefix_products(b2z_ctx* ctx, uint32_t* ext_io, size_t n);
 /* core/poly.rs poly_divide applied to an ext coefficient array on the device (prover.rs runs it on the CPU):
  * in-place synthetic division of `count` AoS ext coefficients by (X - z); remainder -> 4 host words */
 b2z_err b2z_poly_divide(b2z_ctx* ctx, uint32_t* ext_coeffs, size_t count, const uint32_t* z_host, uint32_t* remainder_host);
@@ -126,14 +137,91 @@ b2z_err b2z_witgen(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, uint32_t* c
 b2z_err b2z_prove_segment_device(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, const uint32_t* code_dev,
                                  const uint32_t* data_dev, const uint32_t* globals_host, const uint32_t* accum_noise_dev,
                                  size_t zk_rows, uint32_t* seal_host, size_t* seal_words);
-/* Host buffers in, seal out: H2D of the witness and D2H of the seal happen inside the call. */
+/* Host buffers in, seal out: H2D of the witness and D2H of the seal happen inside the call (pageable or pinned sources,
+ * see below).  A witness that does not satisfy the circuit returns an error. */
 b2z_err b2z_prove_segment(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, const uint32_t* code_host, const uint32_t* data_host,
                           const uint32_t* globals_host, const uint32_t* accum_noise_host, size_t zk_rows, uint32_t* seal_host,
                           size_t* seal_words);
+/* Host buffers in, seal out: H2D of the witness and D2H of the seal happen inside the call, the upload overlapped with
+ * the commits.  Pinned buffers (cudaMallocHost / cudaHostRegister) are copied directly; PAGEABLE buffers (a Rust
+ * Vec<u32>, a numpy array) are detected and staged through a pinned ring by helper threads, so both overlap.
+ * An unsatisfied witness (non-zero DEEP remainder) is an ERROR, not a seal. */
+/* (b2z_prove_segment is declared above) */
+
+/* Control roots (risc0: the control-ID table): the Merkle root that the commitment of a program's code group has at a
+ * given po2.  verify/mod.rs check_code(po2, code_root) binds a seal to the program -- the check behind
+ * receipt.verify(image_id), /root/reference crates/host/src/bin/cli.rs:103.  b2z_compute_control_root derives it on the
+ * GPU from the code columns; b2z_circuit_set_control_root registers it with a circuit (verifier side). */
+b2z_err b2z_compute_control_root(b2z_ctx* ctx, unsigned po2, const uint32_t* code_dev, size_t code_cols, uint32_t* root8_host);
+b2z_err b2z_circuit_set_control_root(b2z_circuit* c, unsigned po2, const uint32_t* root8);
+int b2z_circuit_get_control_root(const b2z_circuit* c, unsigned po2, uint32_t* root8); /* 1 if registered */
+
 /* Per-segment STARK verifier on the host CPU: what `receipt.verify(image_id)` (/root/reference crates/host/src/bin/cli.rs:103)
  * runs for each SegmentReceipt seal (risc0-zkp verify/mod.rs).  Needs no GPU (load the circuit with ctx == NULL).
- * Returns 0 if the seal is accepted, a positive rejection code otherwise, -1 on bad arguments. */
+ * Returns 0 if the seal is accepted, a positive rejection code otherwise, -1 on bad arguments.  Codes: 1-13 transcript /
+ * Merkle / FRI failures, 14 = the seal's code root differs from the registered control root, 15 = no control root is
+ * registered for the seal's po2 (fails closed). */
 int b2z_verify_segment(const b2z_circuit* c, const uint32_t* seal, size_t seal_words);
+
+/* ---- session level: Prover::prove -> Receipt, Receipt::verify (risc0-zkvm 3.0.3; /root/reference
+ * crates/host/src/lib.rs:131-142 and crates/host/src/bin/cli.rs:103-107) ---- */
+/* One segment of a session = the cached witness of SegmentProver::prove's input (noise is an input). */
+typedef struct b2z_segment_input {
+  uint32_t index;              /* position in the session (receipts come back in this order) */
+  uint32_t po2;
+  const uint32_t* code;        /* [code cols][2^po2] */
+  const uint32_t* data;        /* [data cols][2^po2] */
+  const uint32_t* globals;     /* host, always */
+  const uint32_t* accum_noise; /* [accum cols][zk_rows] */
+  size_t zk_rows;
+  int on_device;               /* 0: code/data/accum_noise are host pointers (pinned or pageable); 1: device pointers */
+} b2z_segment_input;
+/* SegmentReceipt{seal, index, hashfn, verifier_parameters, claim} */
+typedef struct b2z_segment_receipt {
+  uint32_t index;
+  uint32_t po2;
+  char hashfn[16];                 /* "poseidon2" */
+  uint32_t verifier_parameters[8]; /* digest naming (proof system, circuit) */
+  uint32_t claim_pre[8];           /* ReceiptClaim stand-in: pre / post state digests (protocol_params.h, synthetic sessions) */
+  uint32_t claim_post[8];
+  uint32_t* seal;                  /* owned by the receipt; the bit-exact Vec<u32> transcript */
+  size_t seal_words;
+} b2z_segment_receipt;
+/* Receipt{inner: Composite{segments, ..}, journal} */
+typedef struct b2z_receipt {
+  b2z_segment_receipt* segments;
+  size_t n_segments;
+  uint32_t verifier_parameters[8];
+  uint8_t* journal;
+  size_t journal_len;
+} b2z_receipt;
+/* A prover server for one circuit on one GPU with `in_flight` (1..8) segments proved concurrently on separate streams. */
+b2z_err b2z_session_create(int device, const uint32_t* blob, size_t words, unsigned in_flight, b2z_session** out);
+b2z_err b2z_session_destroy(b2z_session* s);
+b2z_circuit* b2z_session_circuit(b2z_session* s);               /* worker 0's circuit (seal sizes, verification) */
+b2z_ctx* b2z_session_context(b2z_session* s, unsigned worker);  /* a worker's context (witness generation, buffers) */
+unsigned b2z_session_in_flight(const b2z_session* s);
+b2z_err b2z_session_set_control_root(b2z_session* s, unsigned po2, const uint32_t* root8);
+/* ProverServer::prove_session: every segment proved (one retry on a device error; an unsatisfied witness fails the
+ * session), SegmentReceipts assembled in index order.  Free the result with b2z_receipt_free. */
+b2z_err b2z_prove_session(b2z_session* s, const b2z_segment_input* segments, size_t n_segments, const uint8_t* journal,
+                          size_t journal_len, b2z_receipt** out);
+uint64_t b2z_session_launch_count(const b2z_session* s);
+double b2z_session_last_wall_ms(const b2z_session* s);
+size_t b2z_session_last_retries(const b2z_session* s);
+size_t b2z_session_last_segment_ms(const b2z_session* s, double* ms, size_t cap);
+/* Receipt containers: assemble from seals (claims are decoded from each seal's header), free, (de)serialise. */
+b2z_err b2z_receipt_assemble(const b2z_circuit* c, const uint32_t* const* seals, const size_t* seal_words, size_t n_segments,
+                             const uint8_t* journal, size_t journal_len, b2z_receipt** out);
+b2z_err b2z_receipt_free(b2z_receipt* r);
+b2z_err b2z_receipt_serialize(const b2z_receipt* r, uint8_t** bytes, size_t* len); /* free with b2z_bytes_free */
+b2z_err b2z_receipt_deserialize(const uint8_t* bytes, size_t len, b2z_receipt** out);
+void b2z_bytes_free(uint8_t* bytes);
+/* Receipt::verify(image_id): segments in index order, every seal verified (incl. control root), each claim equal to what
+ * its seal's header says, claims chained (post of i == pre of i + 1), first pre-state == image_id (NULL skips that).
+ * 0 = accepted; 1-15 = b2z_verify_segment code of segment *bad_segment; 101 empty, 102 index order, 103 hashfn,
+ * 104 verifier parameters, 105 claim != seal, 106 claim chain broken, 107 image id mismatch. */
+int b2z_verify_receipt(const b2z_circuit* c, const b2z_receipt* r, const uint32_t* image_id8, size_t* bad_segment);
 /* per-phase device milliseconds of the last prove call on this context (names via b2z_phase_name; returns count) */
 size_t b2z_last_phase_ms(const b2z_ctx* ctx, double* ms, size_t cap);
 const char* b2z_phase_name(size_t i);

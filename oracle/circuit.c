@@ -50,7 +50,18 @@ struct or_circuit {
   uint32_t *pin_col, *pin_global;
   uint8_t *col_kind;     /* per data column: 0 free, 1 free bit, 2 derived */
   size_t n_wit_fp;
+  /* control roots (risc0: control IDs): expected Merkle root of the code group per po2 (verify/mod.rs check_code) */
+  uint32_t control_root[32][8];
+  uint8_t has_control_root[32];
 };
+void or_circuit_set_control_root(or_circuit *c, unsigned po2, const uint32_t *root8) {
+  if (po2 >= 32) return;
+  memcpy(c->control_root[po2], root8, 32);
+  c->has_control_root[po2] = 1;
+}
+const uint32_t *orc_control_root(const or_circuit *c, unsigned po2) {
+  return (po2 < 32 && c->has_control_root[po2]) ? c->control_root[po2] : NULL;
+}
 
 size_t or_circuit_group_size(const or_circuit *c, int g) { return c->group_size[g]; }
 size_t or_circuit_globals_size(const or_circuit *c) { return c->globals_size; }
@@ -373,6 +384,10 @@ void or_witgen(const or_circuit *c, unsigned po2, fp *code, fp *data, fp *global
       data[col * n + r] = v;
     }
   for (size_t g = 0; g < c->globals_size; g++) globals[g] = or_synth_rand(seed, STREAM_FREE, 0xffff, g);
+  /* claim words (protocol_params.h, synthetic sessions): post-state of seed s == pre-state of seed s + 1 */
+  if (pp_claim_post_offset(c->globals_size) >= 0)
+    for (size_t g = (size_t)pp_claim_post_offset(c->globals_size); g < c->globals_size; g++)
+      globals[g] = or_synth_rand(seed + 1, STREAM_FREE, 0xffff, g - PP_CLAIM_DIGEST_WORDS);
   for (size_t i = 0; i < c->n_pins; i++) globals[c->pin_global[i]] = data[(size_t)c->pin_col[i] * n];
   /* derived columns: run the witgen program on every active row (taps read the trace domain, stride 1) */
   const fp *grp[3] = {NULL, code, data};

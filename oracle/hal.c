@@ -226,3 +226,13 @@ void or_to_montgomery(uint32_t *io, size_t n) {
 void or_from_montgomery(uint32_t *io, size_t n) {
   for (size_t i = 0; i < n; i++) io[i] = fp_to_u32(io[i]);
 }
+
+/* hal/cpu.rs scatter [RECALL lo-med]: CSR form, cycle c writes into[offsets[i]] = values[i] for i in [index[c], index[c+1]) */
+void or_scatter(fp *into, const uint32_t *index, const uint32_t *offsets, const fp *values, size_t count) {
+  for (size_t c = 0; c < count; c++)
+    for (uint32_t i = index[c]; i < index[c + 1]; i++) into[offsets[i]] = values[i];
+}
+/* hal/cpu.rs prefix_products [RECALL med]: io[i] = io[0] * ... * io[i] over AoS ext elements */
+void or_prefix_products(fp4 *io, size_t n) {
+  for (size_t i = 1; i < n; i++) io[i] = fp4_mul(io[i - 1], io[i]);
+}

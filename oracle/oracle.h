@@ -21,15 +21,17 @@
 extern "C" {
 #endif
 
-/* protocol constants: risc0-zkp 3.0.2 src/lib.rs */
-#define OR_INV_RATE 4
-#define OR_QUERIES 50
-#define OR_FRI_FOLD 16
-#define OR_FRI_MIN_DEGREE 256
-#define OR_EXT_SIZE 4
-#define OR_CHECK_SIZE 16
-#define OR_DIGEST_WORDS 8
-#define OR_ZK_CYCLES 1994
+/* protocol constants: risc0-zkp 3.0.2 src/lib.rs.  The recalled conventions live in ONE header shared
+ * with the product (values + confidence tags): a real risc0 seal flips them in one place for oracle, prover, verifier. */
+#include "../include/protocol_params.h"
+#define OR_INV_RATE PP_INV_RATE
+#define OR_QUERIES PP_QUERIES
+#define OR_FRI_FOLD PP_FRI_FOLD
+#define OR_FRI_MIN_DEGREE PP_FRI_MIN_DEGREE
+#define OR_EXT_SIZE PP_EXT_SIZE
+#define OR_CHECK_SIZE PP_CHECK_SIZE
+#define OR_DIGEST_WORDS PP_DIGEST_WORDS
+#define OR_ZK_CYCLES PP_ZK_CYCLES
 
 /* ---- Poseidon2 (poseidon2.c) ---- */
 typedef struct {
@@ -66,6 +68,8 @@ void or_eltwise_sum_extelem(fp *out, const fp4 *in, size_t count, size_t to_add)
 void or_eltwise_copy_elem(fp *out, const fp *in, size_t n);
 void or_eltwise_zeroize_elem(fp *io, size_t n);
 void or_gather_sample(fp *dst, const fp *src, size_t idx, size_t size, size_t stride);
+void or_scatter(fp *into, const uint32_t *index, const uint32_t *offsets, const fp *values, size_t count);
+void or_prefix_products(fp4 *io, size_t n);
 /* vectorised field helpers for tests */
 void or_fp_mul_vec(fp *out, const fp *a, const fp *b, size_t n);
 void or_fp4_mul_vec(fp4 *out, const fp4 *a, const fp4 *b, size_t n);
@@ -89,6 +93,11 @@ fp4 or_poly_ext(const or_circuit *c, const fp4 *poly_mix, const fp4 *eval_u, con
 void or_witgen(const or_circuit *c, unsigned po2, fp *code, fp *data, fp *globals, uint64_t seed, size_t zk_rows);
 void or_accumulate(const or_circuit *c, unsigned po2, fp *accum, const fp *code, const fp *data, const fp *mix,
                    const fp *accum_noise, size_t zk_rows);
+
+/* control roots: the verifier rejects (code 14) a seal whose code-group root differs from the registered one and
+ * (code 15) a seal of a po2 that has none registered -- risc0-zkp verify/mod.rs check_code / the control-ID table */
+void or_circuit_set_control_root(or_circuit *c, unsigned po2, const uint32_t *root8);
+void or_control_root(unsigned po2, const fp *code, size_t cols, uint32_t *root8);
 
 /* ---- prover / verifier (zkp.c) ---- */
 /* Returns seal length in words (0 on failure); *seal is malloc'd. timings (optional, 16 doubles) gets per-phase seconds. */

@@ -138,7 +138,7 @@ fp4 or_rng_ext(or_rng *r) {
 }
 uint32_t or_rng_bits(or_rng *r, unsigned bits) {
   uint32_t val = fp_to_u32(or_rng_elem(r));
-  for (int i = 0; i < 3; i++) {
+  for (int i = 0; i < PP_RANDOM_BITS_EXTRA_DRAWS; i++) { /* [RECALL lo-med] */
     uint32_t nv = fp_to_u32(or_rng_elem(r));
     if (val == 0) val = nv;
   }

@@ -18,7 +18,8 @@ P = 15 * (1 << 27) + 1
 
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("bb.c", "poseidon2.c", "hal.c", "circuit.c", "zkp.c", "bb.h", "oracle.h", "poseidon2_consts.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("bb.c", "poseidon2.c", "hal.c", "circuit.c", "zkp.c", "bb.h", "oracle.h", "poseidon2_consts.h",
+                                              "../include/protocol_params.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s", "liboracle.so"])
     return so
@@ -218,6 +219,29 @@ def eltwise_sum_extelem(inp, count):
     return out
 
 
+def scatter(into, index, offsets, values):
+    into = u32(into).copy()
+    index, offsets, values = u32(index), u32(offsets), u32(values)
+    lib().or_scatter(_p(into), _p(index), _p(offsets), _p(values), C.c_size_t(index.size - 1))
+    return into
+
+
+def prefix_products(io):
+    io = u32(io).copy()
+    lib().or_prefix_products(_p(io), C.c_size_t(io.size // 4))
+    return io
+
+
+def control_root(po2, code, cols) -> np.ndarray:
+    """Merkle root of the committed code group (risc0: the control ID of this po2)."""
+    code = u32(code)
+    out = np.empty(8, dtype=np.uint32)
+    L = lib()
+    L.or_control_root.argtypes = [C.c_uint, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.or_control_root(po2, _p(code), cols, _p(out))
+    return out
+
+
 def eltwise_zeroize_elem(io):
     io = u32(io).copy()
     lib().or_eltwise_zeroize_elem(_p(io), C.c_size_t(io.size))
@@ -255,9 +279,20 @@ class Circuit:
         L = lib()
         L.or_witgen.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_size_t]
         L.or_witgen(self.h, po2, _p(code), _p(data), _p(glob), seed, zk_rows)
+        # witgen emits the CANONICAL code columns of (po2, zk_rows): register their Merkle root as this po2's control root
+        # (risc0 ships that table with the circuit; the verifier rejects seals committing to any other code columns)
+        self.set_control_root(po2, control_root(po2, code, wc))
         noise = np.array([L.or_synth_rand(seed, 4, c, r) for c in range(wa) for r in range(zk_rows)], dtype=np.uint32) \
             if wa * zk_rows <= 4096 else synth_rand_array(seed, 4, wa, zk_rows)
         return code, data, glob[: self.globals_size], noise
+
+    def set_control_root(self, po2, root):
+        L = lib()
+        L.or_circuit_set_control_root.argtypes = [C.c_void_p, C.c_uint, C.c_void_p]
+        r = u32(root)
+        L.or_circuit_set_control_root(self.h, po2, _p(r))
+        self.control_roots = getattr(self, "control_roots", {})
+        self.control_roots[po2] = r.copy()
 
     def accumulate(self, po2, code, data, mix, noise, zk_rows):
         n = 1 << po2

@@ -34,6 +34,7 @@ const uint32_t *orc_reg_size(const or_circuit *c);
 const uint32_t *orc_combo_begin(const or_circuit *c);
 const uint32_t *orc_combo_backs(const or_circuit *c);
 const uint8_t *orc_info(const or_circuit *c);
+const uint32_t *orc_control_root(const or_circuit *c, unsigned po2);
 
 static double now_s(void) { return omp_get_wtime(); }
 
@@ -82,11 +83,7 @@ static merkle_params merkle_params_new(size_t row_size, size_t col_size, size_t 
   p.row_size = row_size;
   p.col_size = col_size;
   p.layers = bb_log2(row_size);
-  p.top_layer = 0;
-  for (size_t i = 1; i < p.layers; i++) {
-    if (((size_t)1 << i) > queries) break;
-    p.top_layer = i;
-  }
+  p.top_layer = pp_merkle_top_layer(p.layers, queries); /* [RECALL med] rule lives in protocol_params.h */
   p.top_size = (size_t)1 << p.top_layer;
   return p;
 }
@@ -132,6 +129,8 @@ static int merkle_verifier_new(merkle_verifier *v, read_iop *iop, size_t rows, s
   v->top = (uint32_t *)calloc(2 * ts * 8, 4);
   const uint32_t *p = riop_read(iop, 8 * ts);
   if (!p) return 1;
+  for (size_t i = 0; i < 8 * ts; i++)
+    if (p[i] >= BB_P) return 1; /* hash_pair asserts reduced digest words: a non-canonical word is a malleated seal */
   memcpy(v->top + 8 * ts, p, 32 * ts);
   for (size_t i = ts; i-- > 1;) or_hash_pair(v->top + 8 * (2 * i), v->top + 8 * (2 * i + 1), v->top + 8 * i);
   or_rng_mix(&iop->rng, v->top + 8);
@@ -142,6 +141,8 @@ static const fp *merkle_verify(const merkle_verifier *v, read_iop *iop, size_t i
   if (idx >= v->params.row_size) return NULL;
   const fp *row = riop_read(iop, v->params.col_size);
   if (!row) return NULL;
+  for (size_t i = 0; i < v->params.col_size; i++)
+    if (row[i] >= BB_P) return NULL;
   uint32_t cur[8], tmp[8];
   or_hash_elem_slice(row, v->params.col_size, cur);
   idx += v->params.row_size;
@@ -149,6 +150,8 @@ static const fp *merkle_verify(const merkle_verifier *v, read_iop *iop, size_t i
     size_t low = idx & 1;
     const uint32_t *other = riop_read(iop, 8);
     if (!other) return NULL;
+    for (int i = 0; i < 8; i++)
+      if (other[i] >= BB_P) return NULL; /* non-canonical sibling digest: reject (seal malleability) */
     idx /= 2;
     if (low) or_hash_pair(other, cur, tmp);
     else or_hash_pair(cur, other, tmp);
@@ -191,6 +194,20 @@ static void commit_group(poly_group *pg, write_iop *iop, const fp *witness, size
   merkle_commit(&pg->merkle, iop);
 }
 
+/* Control root of a code group: the Merkle root its commitment will have in any honest seal (risc0 ships these per po2
+ * as the control-ID table; verify/mod.rs check_code compares the seal's code root against it). */
+void or_control_root(unsigned po2, const fp *code, size_t cols, uint32_t *root8) {
+  size_t n = (size_t)1 << po2;
+  poly_group pg;
+  fp *coeffs = (fp *)malloc(4 * cols * n);
+  memcpy(coeffs, code, 4 * cols * n);
+  or_batch_interpolate_ntt(coeffs, cols, n);
+  or_zk_shift(coeffs, cols, n);
+  poly_group_new(&pg, coeffs, cols, n);
+  memcpy(root8, merkle_root(&pg.merkle), 32);
+  poly_group_free(&pg);
+}
+
 /* ---------------- small polynomial helpers (core/poly.rs) ---------------- */
 static fp4 poly_eval(const fp4 *coeffs, size_t n, fp4 x) {
   fp4 tot = fp4_zero();
@@ -199,8 +216,8 @@ static fp4 poly_eval(const fp4 *coeffs, size_t n, fp4 x) {
 }
 /* unique interpolant through (x_i, fx_i), Newton form expanded to monomial coefficients */
 static void poly_interpolate(fp4 *out, const fp4 *x, const fp4 *fx, size_t size) {
-  fp4 basis[10], dd[10];
-  if (size > 8) abort();
+  fp4 basis[18], dd[18];
+  if (size > 16) abort();
   for (size_t i = 0; i < size; i++) dd[i] = fx[i];
   for (size_t j = 1; j < size; j++)
     for (size_t i = size - 1; i >= j; i--) dd[i] = fp4_mul(fp4_sub(dd[i], dd[i - 1]), fp4_inv(fp4_sub(x[i], x[i - j])));
@@ -288,11 +305,11 @@ typedef struct {
 } inner_ctx;
 static void inner_prove(void *vctx, write_iop *iop, size_t idx) {
   inner_ctx *c = (inner_ctx *)vctx;
-  for (int g = 0; g < 3; g++) merkle_prove(&c->groups[g]->merkle, iop, idx);
+  for (int k = 0; k < 3; k++) merkle_prove(&c->groups[PP_QUERY_ORDER[k]]->merkle, iop, idx); /* [RECALL med] */
   merkle_prove(&c->check->merkle, iop, idx);
 }
 
-static const char PROOF_SYSTEM_INFO[16] = {'R', 'I', 'S', 'C', '0', '_', 'S', 'T', 'A', 'R', 'K', ':', 'v', '1', '_', '_'};
+static const char PROOF_SYSTEM_INFO[PP_INFO_BYTES + 1] = PP_PROOF_SYSTEM_INFO; /* [RECALL med] protocol_params.h */
 static void hash_info(const uint8_t *info, uint32_t *dg) {
   fp e[16];
   for (int i = 0; i < 16; i++) e[i] = fp_from_u32(info[i]);
@@ -526,6 +543,11 @@ int or_verify_segment(const or_circuit *c, const uint32_t *seal, size_t seal_wor
   fp4 *eval_u = NULL, *combo_u = NULL, *tap_mix_pows = NULL, *tot = NULL, *poly_buf = NULL;
 #define FAIL(code) do { rc_ = (code); goto done; } while (0)
   if (merkle_verifier_new(&mv[G_CODE], &iop, domain, wc)) FAIL(4);
+  { /* verify/mod.rs check_code(po2, code_merkle.root()): the seal must commit to THIS program's code columns */
+    const uint32_t *want = orc_control_root(c, po2);
+    if (!want) FAIL(15);
+    if (memcmp(want, mv[G_CODE].top + 8, 32) != 0) FAIL(14);
+  }
   if (merkle_verifier_new(&mv[G_DATA], &iop, domain, wd)) FAIL(4);
   mix = (fp *)malloc(4 * (msz + 1));
   for (size_t i = 0; i < msz; i++) mix[i] = or_rng_elem(&iop.rng);
@@ -551,7 +573,7 @@ int or_verify_segment(const or_circuit *c, const uint32_t *seal, size_t seal_wor
     }
   fp4 result = or_poly_ext(c, &poly_mix, eval_u, globals, mix);
   {
-    static const int remap[4] = {0, 2, 1, 3};
+    const int *remap = PP_CHECK_REMAP; /* [RECALL med] */
     fp4 check = fp4_zero();
     for (int i = 0; i < 4; i++) {
       fp4 zi = fp4_pow(z, (uint64_t)i);
@@ -615,7 +637,8 @@ int or_verify_segment(const or_circuit *c, const uint32_t *seal, size_t seal_wor
       /* inner: open all groups at pos and form the DEEP quotient value (verify/mod.rs fri_eval_taps) */
       fp4 x = fp4_from_fp(fp_pow(gen0, pos));
       const fp *rows[3];
-      for (int g = 0; g < 3; g++) {
+      for (int k = 0; k < 3; k++) { /* [RECALL med] opening order: protocol_params.h PP_QUERY_ORDER */
+        int g = PP_QUERY_ORDER[k];
         rows[g] = merkle_verify(&mv[g], &iop, pos);
         if (!rows[g]) FAIL(9);
       }

@@ -94,6 +94,8 @@ def test_product_verifier_matches_oracle_verifier(oracle):
         zk = min(1994, n // 4)
         code, data, glob, noise = oc.witgen(po2, 31 + po2, zk)
         seal = oc.prove(po2, code, data, glob, noise, zk)
+        assert c.verify(seal) == 15  # fails closed: no control root registered for this po2 yet
+        c.set_control_root(po2, oc.control_roots[po2])
         assert c.verify(seal) == 0 and oc.verify(seal) == 0
         rng = np.random.default_rng(po2)
         for pos in list(rng.integers(0, seal.size, size=25)) + [0, sc.globals_size, seal.size - 1]:
@@ -128,3 +130,76 @@ def test_host_poseidon2_f64_stream_is_bit_exact():
         L.b2z_host_poseidon2_mix(a.ctypes.data_as(C.c_void_p))
         L.b2z_host_poseidon2_mix_f64(b.ctypes.data_as(C.c_void_p))
         assert np.array_equal(a, b)
+
+
+def test_verifier_binds_the_code_group_to_the_control_root(oracle):
+    """receipt.verify(image_id) binds a seal to the PROGRAM (risc0-zkp verify/mod.rs check_code): a prover that commits
+    to its own code columns -- e.g. the two selectors zeroed on every row, which makes every selector-gated
+    constraint vanish -- must be rejected even though everything else in its seal is consistent."""
+    sc = S.circuit_small()
+    po2, zk = 9, 128
+    oc = oracle.Circuit(sc.blob)
+    c = H.Circuit(None, sc.blob)
+    code, data, glob, noise = oc.witgen(po2, 17, zk)
+    c.set_control_root(po2, oc.control_roots[po2])
+    honest = oc.prove(po2, code, data, glob, noise, zk)
+    assert c.verify(honest) == 0 == oc.verify(honest)
+    forged_code = code.copy()
+    forged_code[: 2 << po2] = 0  # code columns 0 / 1 = the `active` and `first` selectors -> 0 everywhere
+    rng = np.random.default_rng(3)
+    garbage = rng.integers(0, 15 * (1 << 27) + 1, size=data.size, dtype=np.uint64).astype(np.uint32)  # satisfies nothing
+    forged = oc.prove(po2, forged_code, garbage, glob, noise, zk)
+    assert c.verify(forged) == 14 == oc.verify(forged)
+    # the same forged seal is "valid" for a verifier that trusts the prover's code columns: that is the hole being closed
+    c2 = H.Circuit(None, sc.blob)
+    c2.set_control_root(po2, oracle.control_root(po2, forged_code, sc.w_code))
+    assert c2.verify(forged) == 0
+    c.close()
+    c2.close()
+
+
+def test_noncanonical_digest_words_are_rejected(oracle):
+    """Merkle digests are field elements: x + P hashes like x, so a verifier that accepts unreduced words lets several
+    distinct seals verify for one proof (upstream's hash_pair asserts reduced inputs)."""
+    P = 15 * (1 << 27) + 1
+    sc = S.circuit_tiny()
+    po2, zk = 8, 64
+    oc = oracle.Circuit(sc.blob)
+    c = H.Circuit(None, sc.blob)
+    code, data, glob, noise = oc.witgen(po2, 5, zk)
+    c.set_control_root(po2, oc.control_roots[po2])
+    seal = oc.prove(po2, code, data, glob, noise, zk)
+    assert c.verify(seal) == 0
+    hits = 0
+    top0 = sc.globals_size + 1  # first word of the code tree's top layer
+    for pos in [top0, top0 + 9, seal.size - 3, seal.size - 20]:
+        if int(seal[pos]) + P < (1 << 32):
+            bad = seal.copy()
+            bad[pos] = np.uint32(int(seal[pos]) + P)
+            assert c.verify(bad) != 0 and oc.verify(bad) != 0
+            hits += 1
+    assert hits >= 2
+
+
+def test_malformed_circuit_blobs_are_rejected():
+    """circuit_parse validates every operand the verifier / generated kernels index with."""
+    sc = S.circuit_tiny()
+    blob = sc.blob
+    n_taps, n_steps = int(blob[7]), int(blob[8])
+    steps0 = 24 + n_taps
+    ops = blob[steps0: steps0 + 5 * n_steps].reshape(-1, 5)
+    gg = [i for i in range(n_steps) if ops[i, 0] == S.OP_GET_GLOBAL]
+    assert gg
+    for field, value in ((1, 2), (2, 1 << 20)):  # selector out of {globals, mix}; offset past the table
+        bad = blob.copy()
+        bad[steps0 + 5 * gg[0] + field] = value
+        with pytest.raises(H.B2ZError, match="GetGlobal"):
+            H.Circuit(None, bad)
+    # duplicate back inside a register (taps stay sorted): DEEP interpolation would divide by zero
+    taps = blob[24: 24 + n_taps]
+    same = [i for i in range(1, n_taps) if (taps[i] & 0xff00ffff) == (taps[i - 1] & 0xff00ffff)]
+    assert same
+    bad = blob.copy()
+    bad[24 + same[0]] = taps[same[0] - 1]
+    with pytest.raises(H.B2ZError, match="strictly increasing"):
+        H.Circuit(None, bad)

@@ -326,3 +326,99 @@ def test_hash_rows_chunk_rejects_ragged_middle_chunk(hal):
         hal.hash_rows_chunk(do, dm, 64, 20, carry_in=False, last=False)
     hal.free(do)
     hal.free(dm)
+
+
+# ---- BASELINE config-5 shapes: 256-column launches (grid.y / 32-bit index guards), full compare against the oracle ----
+def test_config5_shape_po2_20_cols_256(hal, oracle):
+    """(po2, cols) = (20, 256): iNTT, x4 expand-NTT and hash_rows on the resulting [256][2^22] LDE matrix, every word
+    against the oracle (1 GiB in, 4 GiB LDE, 2^22 leaves x 16 permutations)."""
+    po2, cols = 20, 256
+    n = 1 << po2
+    rng = np.random.default_rng(0xB2000005)
+    x = rng.integers(0, P, size=cols * n, dtype=np.uint32)  # uniform in [0, P) up to a 2^-32-scale bias: fine for parity
+    d = hal.copy_from(x)
+    hal.batch_interpolate_ntt(d, cols, po2)
+    coeffs = hal.view(d, x.size)
+    want_c = oracle.batch_interpolate_ntt(x, cols)
+    assert np.array_equal(coeffs, want_c)
+    del x, coeffs
+    o = hal.alloc(cols * 4 * n)
+    hal.batch_expand_into_evaluate_ntt(o, d, cols, po2, 2)
+    want_lde = oracle.batch_expand_into_evaluate_ntt(want_c, cols, 2)
+    del want_c
+    # compare in column slabs to bound host memory
+    slab = 32
+    for c0 in range(0, cols, slab):
+        got = np.empty(slab * 4 * n, dtype=np.uint32)
+        import ctypes as C
+        assert not hal.L.b2z_d2h(hal.ctx, got.ctypes.data_as(C.c_void_p), C.c_void_p(o + 4 * c0 * 4 * n), C.c_size_t(4 * got.size))
+        assert np.array_equal(got, want_lde[c0 * 4 * n:(c0 + slab) * 4 * n]), f"LDE columns {c0}..{c0 + slab}"
+    del got
+    rows = 4 * n
+    dig = hal.alloc(8 * rows)
+    hal.hash_rows(dig, o, rows, cols)
+    got_d = hal.view(dig, 8 * rows)
+    assert np.array_equal(got_d, oracle.hash_rows(want_lde, rows, cols))
+    for p in (d, o, dig):
+        hal.free(p)
+
+
+@pytest.mark.parametrize("out_size", [1, 2, 64, 512, 1024, 4096, 1 << 17, 1 << 20])
+def test_hash_fold_direct(hal, oracle, out_size):
+    """Hal::hash_fold(io, in_size, out_size) on its own: single-CTA sizes, thread-per-parent sizes and (2^20 parents) the
+    mixed INT/FP64 persistent kernel."""
+    rng = np.random.default_rng(900 + out_size.bit_length())
+    nodes = np.zeros(8 * 4 * out_size, dtype=np.uint32)
+    nodes[8 * 2 * out_size:] = rand_fp(rng, 8 * 2 * out_size)
+    d = hal.copy_from(nodes)
+    hal.hash_fold(d, 2 * out_size, out_size)
+    got = hal.view(d, nodes.size)
+    hal.free(d)
+    want = oracle.hash_fold(nodes, 2 * out_size, out_size)
+    assert np.array_equal(got, want)
+    assert np.any(want[8 * out_size: 16 * out_size])
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 1023, 1024, 1025, 70000, (1 << 20) + 3])
+def test_prefix_products(hal, oracle, n):
+    rng = np.random.default_rng(n)
+    x = rand_fp(rng, 4 * n)
+    d = hal.copy_from(x)
+    hal.prefix_products(d, n)
+    got = hal.view(d, 4 * n)
+    hal.free(d)
+    assert np.array_equal(got, oracle.prefix_products(x))
+
+
+def test_scatter(hal, oracle):
+    rng = np.random.default_rng(77)
+    count, size = 5000, 1 << 16
+    per = rng.integers(0, 6, size=count)
+    index = np.concatenate([[0], np.cumsum(per)]).astype(np.uint32)
+    total = int(index[-1])
+    offsets = rng.permutation(size)[:total].astype(np.uint32)  # distinct targets: the result does not depend on thread order
+    offsets[3] = offsets[2] if per[0] >= 4 else offsets[3]     # except inside one cycle, where the later entry wins
+    values = rand_fp(rng, total)
+    into = rand_fp(rng, size)
+    di, dx, do_, dv = hal.copy_from(into), hal.copy_from(index), hal.copy_from(offsets), hal.copy_from(values)
+    hal.scatter(di, dx, do_, dv, count)
+    got = hal.view(di, size)
+    for p in (di, dx, do_, dv):
+        hal.free(p)
+    assert np.array_equal(got, oracle.scatter(into, index, offsets, values))
+    hal.scatter(0, 0, 0, 0, 0)  # empty: no-op
+
+
+def test_negative_c_abi_arguments(hal):
+    """Error returns (not crashes) for malformed calls through the C ABI."""
+    import ctypes as C
+    from zeth_b200 import hal as H
+    L = hal.L
+    d = hal.alloc(1024)
+    assert b"exceeds" in L.b2z_batch_interpolate_ntt(hal.ctx, C.c_void_p(d), C.c_size_t(1), C.c_uint(27))
+    assert b"distinct" in L.b2z_batch_expand_into_evaluate_ntt(hal.ctx, C.c_void_p(d), C.c_void_p(d), C.c_size_t(1), C.c_uint(4), C.c_uint(2))
+    assert b"power of two" in L.b2z_merkle_build(hal.ctx, C.c_void_p(d), C.c_void_p(d), C.c_size_t(12), C.c_size_t(2))
+    assert b"must not be empty" in L.b2z_hash_rows_chunk(hal.ctx, C.c_void_p(d), C.c_void_p(d), C.c_size_t(16), C.c_size_t(0), C.c_int(1), C.c_int(1))
+    with pytest.raises(H.B2ZError, match="in_flight"):
+        H.Session(0, np.zeros(64, dtype=np.uint32), in_flight=0)
+    hal.free(d)

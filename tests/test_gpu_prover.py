@@ -23,6 +23,7 @@ def test_seal_parity_host_api(hal, oracle, mk, po2):
     oc, code, data, glob, noise, zk = _witness(oracle, sc, po2, 11 + po2)
     want = oc.prove(po2, code, data, glob, noise, zk)
     c = H.Circuit(hal, sc.blob)
+    c.set_control_root(po2, oc.control_roots[po2])  # the ORACLE's control root: the product verifier must agree with it
     got = hal.prove_segment(c, po2, code, data, glob, noise, zk)
     assert got.size == want.size
     diff = np.nonzero(got != want)[0]
@@ -113,8 +114,11 @@ def test_full_gpu_pipeline_witgen_to_seal(hal, oracle):
     hal.witgen(c, po2, dcode, ddata, dglob, dnoise, seed, zk)
     glob = hal.view(dglob, sc.globals_size)
     seal = hal.prove_segment_device(c, po2, dcode, ddata, glob, dnoise, zk)
+    root = hal.compute_control_root(po2, dcode, wc)
+    c.set_control_root(po2, root)
     assert c.verify(seal) == 0
     oc, code, data, oglob, noise, _ = _witness(oracle, sc, po2, seed)
+    assert np.array_equal(root, oc.control_roots[po2])  # GPU-derived control root == the oracle's
     assert np.array_equal(glob, oglob)
     assert np.array_equal(seal, oc.prove(po2, code, data, oglob, noise, zk))
     c.close()
@@ -137,6 +141,8 @@ def test_baseline_size_segments_verify(hal, po2):
     glob = hal.view(dglob, sc.globals_size)
     seal = hal.prove_segment_device(c, po2, dcode, ddata, glob, dnoise, zk)
     assert seal.size == c.seal_words(po2)
+    assert c.verify(seal) == 15  # no control root yet: fails closed
+    c.set_control_root(po2, hal.compute_control_root(po2, dcode, wc))
     assert c.verify(seal) == 0
     bad = seal.copy()
     bad[seal.size - 7] ^= 2
@@ -175,7 +181,153 @@ def test_host_and_device_api_agree_at_mixed_kernel_sizes(hal):
     dev = hal.prove_segment_device(c, po2, dcode, ddata, glob, dnoise, zk)
     host = hal.prove_segment(c, po2, code, data, glob, noise, zk)
     assert np.array_equal(dev, host)
+    c.set_control_root(po2, hal.compute_control_root(po2, dcode, wc))
     assert c.verify(host) == 0
     for p in (dcode, ddata, dglob, dnoise):
         hal.free(p)
     c.close()
+
+
+# ---- BASELINE sizes: the shipping hot-path configuration (mixed INT/FP64 hash kernels, multi-pass NTT plans, chunked
+# ---- leaf hashing) inside seals that are compared with the oracle ----
+def _gpu_witness(hal, c, sc, po2, seed, zk=1994):
+    n = 1 << po2
+    wa, wc, wd = sc.group_sizes
+    dcode, ddata = hal.alloc(wc * n), hal.alloc(wd * n)
+    dglob, dnoise = hal.alloc(sc.globals_size), hal.alloc(wa * zk)
+    hal.witgen(c, po2, dcode, ddata, dglob, dnoise, seed, zk)
+    return dcode, ddata, dglob, dnoise, hal.view(dglob, sc.globals_size)
+
+
+@pytest.mark.parametrize("po2,seed", [(18, 0xB2000012), (20, 0xB2000000 + 1000)])
+def test_seal_parity_vs_live_oracle_at_baseline_sizes(hal, oracle, po2, seed):
+    """po2 = 18 and po2 = 20 (BASELINE configs[2..3] segment size), W = 256: the whole seal, word for word, against the
+    oracle run on the box's host cores -- through BOTH entry points (device-resident witness; host buffers, which are
+    pageable numpy arrays here and therefore take the staged-upload path with chunk-carried leaf hashing)."""
+    sc = S.circuit_planning()
+    oc, code, data, glob, noise, zk = _witness(oracle, sc, po2, seed)
+    want = oc.prove(po2, code, data, glob, noise, zk)
+    assert oc.verify(want) == 0
+    c = H.Circuit(hal, sc.blob)
+    c.set_control_root(po2, oc.control_roots[po2])
+    dcode, ddata, dnoise = hal.copy_from(code), hal.copy_from(data), hal.copy_from(noise)
+    got = hal.prove_segment_device(c, po2, dcode, ddata, glob, dnoise, zk)
+    diff = np.nonzero(got != want)[0]
+    assert got.size == want.size and diff.size == 0, f"device API: first differing seal words {diff[:5]} of {want.size}"
+    for p in (dcode, ddata, dnoise):
+        hal.free(p)
+    got = hal.prove_segment(c, po2, code, data, glob, noise, zk)
+    diff = np.nonzero(got != want)[0]
+    assert diff.size == 0, f"host API: first differing seal words {diff[:5]} of {want.size}"
+    assert c.verify(got) == 0
+    c.close()
+
+
+def test_golden_seal_digests_at_baseline_sizes(hal):
+    """BASELINE configs[1] ("Receipt bytes bit-exact vs CPU run"): the po2 = 22 seal of the planning circuit on seed
+    0xB2000002 -- plus po2 18 / 20 -- must hash to the digest the ORACLE produced for the same cached witness
+    (tests/golden/oracle_seals_big.json, frozen by tools/make_golden.py --big: the oracle needs ~10 minutes and ~35 GB
+    for po2 = 22, so later runs only hash).  Device-resident and host-buffer (pageable -> staged) entry points."""
+    import hashlib
+    import json
+    import os
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_seals_big.json")))
+    sc = S.circuit_planning()
+    assert {c["po2"] for c in gold["cases"]} >= {20, 22}
+    for case in gold["cases"]:
+        assert case["blob_sha256"] == hashlib.sha256(sc.blob.tobytes()).hexdigest()
+        po2, zk = case["po2"], case["zk_rows"]
+        n = 1 << po2
+        wa, wc, wd = sc.group_sizes
+        c = H.Circuit(hal, sc.blob)
+        dcode, ddata, dglob, dnoise, glob = _gpu_witness(hal, c, sc, po2, case["seed"], zk)
+        seal = hal.prove_segment_device(c, po2, dcode, ddata, glob, dnoise, zk)
+        assert seal.size == case["seal_words"]
+        assert hashlib.sha256(seal.tobytes()).hexdigest() == case["sha256"], f"po2 {po2}: device-API seal differs from the oracle's"
+        c.set_control_root(po2, hal.compute_control_root(po2, dcode, wc))
+        assert c.verify(seal) == 0
+        code, data, noise = hal.view(dcode, wc * n), hal.view(ddata, wd * n), hal.view(dnoise, wa * zk)
+        for p in (dcode, ddata, dglob, dnoise):
+            hal.free(p)
+        seal2 = hal.prove_segment(c, po2, code, data, glob, noise, zk)
+        assert hashlib.sha256(seal2.tobytes()).hexdigest() == case["sha256"], f"po2 {po2}: host-API seal differs from the oracle's"
+        del code, data, noise
+        c.close()
+
+
+def test_unsatisfied_witness_is_an_error_not_a_seal(hal, oracle):
+    """prover.rs asserts exact DEEP divisions; a witness that violates a constraint must fail the call."""
+    sc = S.circuit_small()
+    po2 = 10
+    oc, code, data, glob, noise, zk = _witness(oracle, sc, po2, 21)
+    c = H.Circuit(hal, sc.blob)
+    assert hal.prove_segment(c, po2, code, data, glob, noise, zk).size == c.seal_words(po2)
+    derived = [col for col in range(sc.w_data) if sc.blob[-sc.w_data:][col] == 2]
+    bad = data.copy()
+    bad[derived[0] * (1 << po2) + 5] ^= 1
+    with pytest.raises(H.B2ZError, match="does not satisfy"):
+        hal.prove_segment(c, po2, code, bad, glob, noise, zk)
+    dcode, ddata, dnoise = hal.copy_from(code), hal.copy_from(bad), hal.copy_from(noise)
+    with pytest.raises(H.B2ZError, match="does not satisfy"):
+        hal.prove_segment_device(c, po2, dcode, ddata, glob, dnoise, zk)
+    # the context stays usable
+    assert np.array_equal(hal.prove_segment(c, po2, code, data, glob, noise, zk), oc.prove(po2, code, data, glob, noise, zk))
+    c.close()
+
+
+def test_pinned_and_pageable_host_buffers_agree(hal, oracle):
+    """b2z_prove_segment detects pageable sources and stages them through its pinned ring: same seal as from pinned memory."""
+    import torch
+    sc = S.circuit_planning()
+    po2 = 14
+    oc, code, data, glob, noise, zk = _witness(oracle, sc, po2, 0xB2000007)
+    want = oc.prove(po2, code, data, glob, noise, zk)
+    c = H.Circuit(hal, sc.blob)
+    pageable = hal.prove_segment(c, po2, code, data, glob, noise, zk)
+    pc, pd, pn = (torch.from_numpy(x.view(np.int32)).pin_memory() for x in (code, data, noise))
+    pinned = hal.prove_segment(c, po2, pc.data_ptr(), pd.data_ptr(), glob, pn.data_ptr(), zk)
+    assert np.array_equal(pageable, want) and np.array_equal(pinned, want)
+    c.close()
+
+
+def test_prove_session_receipts(hal, oracle):
+    """ProverServer::prove_session behind the C ABI: 5 consecutive segments, two in flight, device-resident and host
+    witnesses mixed; receipts come back in index order with the oracle's seals, the claim chain verifies, and a bad
+    witness fails the session naming its segment."""
+    sc = S.circuit_planning()
+    po2, zk, seed0 = 12, 1024, 0xB2000000 + 1000
+    oc = oracle.Circuit(sc.blob)
+    sess = H.Session(0, sc.blob, in_flight=2)
+    wit, want, keep = [], [], []
+    for i in range(5):
+        code, data, glob, noise = oc.witgen(po2, seed0 + i, zk)
+        want.append(oc.prove(po2, code, data, glob, noise, zk))
+        if i % 2 == 0:
+            h = sess.hals[0]
+            dc, dd, dn = h.copy_from(code), h.copy_from(data), h.copy_from(noise)
+            keep += [dc, dd, dn]
+            wit.append(dict(po2=po2, code=dc, data=dd, globals=glob, accum_noise=dn, zk_rows=zk, on_device=True))
+        else:
+            wit.append(dict(po2=po2, code=code, data=data, globals=glob, accum_noise=noise, zk_rows=zk, on_device=False))
+    sess.set_control_root(po2, oc.control_roots[po2])
+    r = sess.prove(wit, journal=b"blockhash")
+    assert r.n_segments == 5 and r.journal == b"blockhash"
+    for i in range(5):
+        assert r.segment(i).index == i
+        assert np.array_equal(r.seal(i), want[i]), f"segment {i}"
+    image_id = wit[0]["globals"][16:24]
+    assert sess.circuit.verify_receipt(r, image_id) == (0, 0)
+    r2 = H.Receipt.deserialize(r.serialize())
+    assert sess.circuit.verify_receipt(r2, image_id) == (0, 0)
+    # a violated constraint in segment 3 fails the whole session and names the segment
+    derived = [col for col in range(sc.w_data) if sc.blob[-sc.w_data:][col] == 2]
+    bad = wit[3]["data"].copy()
+    bad[derived[0] * (1 << po2) + 7] ^= 1
+    wit_bad = list(wit)
+    wit_bad[3] = dict(wit[3], data=bad)
+    with pytest.raises(H.B2ZError, match="segment 3.*does not satisfy"):
+        sess.prove(wit_bad)
+    # and the session is still usable afterwards
+    r3 = sess.prove(wit[:2])
+    assert np.array_equal(r3.seal(1), want[1])
+    sess.close()

@@ -20,6 +20,7 @@ b2z_err witgen_launch(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, uint32_t
 const char* phase_name(size_t i);
 void ntt_release_tables(b2z_ctx* ctx);
 int verify_segment(const b2z_circuit* c, const uint32_t* seal, size_t seal_words);
+b2z_err compute_control_root(b2z_ctx* ctx, unsigned po2, const uint32_t* code_dev, size_t cols, uint32_t* root_host);
 }  // namespace b2z
 using namespace b2z;
 
@@ -60,6 +61,8 @@ b2z_err b2z_destroy(b2z_ctx* ctx) {
   for (int i = 0; i <= MAX_PO2; i++)
     if (ctx->pow3rev[i]) cudaFree(ctx->pow3rev[i]);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->stage_ring) cudaFreeHost(ctx->stage_ring);
+  for (auto e : ctx->stage_events) cudaEventDestroy(e);
   if (ctx->hash_sched) cudaFree(ctx->hash_sched);
   for (auto& pr : ctx->phase_events) {
     cudaEventDestroy(pr.first);
@@ -73,39 +76,50 @@ b2z_err b2z_destroy(b2z_ctx* ctx) {
 }
 b2z_err b2z_set_stream(b2z_ctx* ctx, void* s) {
   B2Z_REQUIRE(ctx, "null context");
+  B2Z_CUDA(cudaSetDevice(ctx->device));
   B2Z_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
   return nullptr;
 }
 b2z_err b2z_sync(b2z_ctx* ctx) {
   B2Z_REQUIRE(ctx, "null context");
+  B2Z_CUDA(cudaSetDevice(ctx->device));
   B2Z_CUDA(cudaStreamSynchronize(ctx->stream));
   return nullptr;
 }
 b2z_err b2z_alloc(b2z_ctx* ctx, size_t bytes, void** dev) {
   B2Z_REQUIRE(ctx && dev, "null argument");
+  B2Z_CUDA(cudaSetDevice(ctx->device));
   B2Z_CUDA(cudaMallocAsync(dev, bytes ? bytes : 4, ctx->stream));
   return nullptr;
 }
 b2z_err b2z_free(b2z_ctx* ctx, void* dev) {
   B2Z_REQUIRE(ctx, "null context");
+  B2Z_CUDA(cudaSetDevice(ctx->device));
   if (dev) B2Z_CUDA(cudaFreeAsync(dev, ctx->stream));
   return nullptr;
 }
 b2z_err b2z_h2d(b2z_ctx* ctx, void* dev, const void* host, size_t bytes) {
   B2Z_REQUIRE(ctx, "null context");
+  B2Z_CUDA(cudaSetDevice(ctx->device));
   B2Z_CUDA(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
   return nullptr;
 }
 b2z_err b2z_d2h(b2z_ctx* ctx, void* host, const void* dev, size_t bytes) {
   B2Z_REQUIRE(ctx, "null context");
+  B2Z_CUDA(cudaSetDevice(ctx->device));
   B2Z_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   B2Z_CUDA(cudaStreamSynchronize(ctx->stream));
   return nullptr;
 }
 uint64_t b2z_launch_count(const b2z_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
-#define CTX_GUARD() B2Z_REQUIRE(ctx != nullptr, "null context (b2z_init failed? there is no CPU fallback)")
+// every entry point re-asserts the context's device: the calling thread may not be the one that ran b2z_init
+#define CTX_GUARD()                                                                          \
+  do {                                                                                       \
+    B2Z_REQUIRE(ctx != nullptr, "null context (b2z_init failed? there is no CPU fallback)"); \
+    B2Z_CUDA(cudaSetDevice(ctx->device));                                                    \
+  } while (0)
 
 b2z_err b2z_batch_interpolate_ntt(b2z_ctx* ctx, uint32_t* io, size_t count, unsigned po2) {
   CTX_GUARD();
@@ -181,6 +195,14 @@ b2z_err b2z_eltwise_zeroize_elem(b2z_ctx* ctx, uint32_t* io, size_t n) {
 b2z_err b2z_gather_sample(b2z_ctx* ctx, uint32_t* dst, const uint32_t* src, size_t idx, size_t size, size_t stride) {
   CTX_GUARD();
   return launch_gather_sample(ctx, dst, src, idx, size, stride);
+}
+b2z_err b2z_scatter(b2z_ctx* ctx, uint32_t* into, const uint32_t* index, const uint32_t* offsets, const uint32_t* values, size_t count) {
+  CTX_GUARD();
+  return launch_scatter(ctx, into, index, offsets, values, count);
+}
+b2z_err b2z_prefix_products(b2z_ctx* ctx, uint32_t* ext_io, size_t n) {
+  CTX_GUARD();
+  return launch_prefix_products(ctx, ext_io, n);
 }
 b2z_err b2z_poly_divide(b2z_ctx* ctx, uint32_t* ext_coeffs, size_t count, const uint32_t* z_host, uint32_t* remainder_host) {
   CTX_GUARD();
@@ -268,6 +290,23 @@ b2z_err b2z_prove_segment(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, cons
   CTX_GUARD();
   B2Z_REQUIRE(c && seal_host, "null argument");
   return prove_segment_host(ctx, c, po2, code_host, data_host, globals_host, accum_noise_host, zk_rows, seal_host, seal_words);
+}
+b2z_err b2z_compute_control_root(b2z_ctx* ctx, unsigned po2, const uint32_t* code_dev, size_t code_cols, uint32_t* root8_host) {
+  CTX_GUARD();
+  B2Z_REQUIRE(code_dev && root8_host, "null argument");
+  return compute_control_root(ctx, po2, code_dev, code_cols, root8_host);
+}
+b2z_err b2z_circuit_set_control_root(b2z_circuit* c, unsigned po2, const uint32_t* root8) {
+  B2Z_REQUIRE(c && root8, "null argument");
+  B2Z_REQUIRE(po2 >= 1 && po2 < 32, "po2 out of range");
+  memcpy(c->control_root[po2], root8, 32);
+  c->has_control_root[po2] = true;
+  return nullptr;
+}
+int b2z_circuit_get_control_root(const b2z_circuit* c, unsigned po2, uint32_t* root8) {
+  if (!c || po2 >= 32 || !c->has_control_root[po2]) return 0;
+  if (root8) memcpy(root8, c->control_root[po2], 32);
+  return 1;
 }
 size_t b2z_last_phase_ms(const b2z_ctx* ctx, double* ms, size_t cap) {
   if (!ctx) return 0;

@@ -9,6 +9,7 @@
 
 #include <dlfcn.h>
 #include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cstring>
@@ -83,6 +84,10 @@ b2z_err circuit_parse(b2z_circuit* c, const uint32_t* blob, size_t words) {
     c->reg_offset.push_back(c->tap_offset[i]);
     c->reg_tap_pos.push_back((uint32_t)i);
     c->reg_size.push_back((uint32_t)(j - i));
+    // DEEP interpolates a register's evaluations at z * w^-back: duplicate backs would divide by zero (fp4_inv(0) = 0 and a
+    // silently wrong U polynomial); the prover's interpolation buffers hold 16 points
+    B2Z_REQUIRE(j - i <= 16, "circuit blob: a register has more than 16 taps");
+    for (size_t k = i + 1; k < j; k++) B2Z_REQUIRE(c->tap_back[k] > c->tap_back[k - 1], "circuit blob: a register's backs are not strictly increasing");
     i = j;
   }
   size_t nr = c->reg_group.size();
@@ -141,8 +146,28 @@ b2z_err circuit_parse(b2z_circuit* c, const uint32_t* blob, size_t words) {
       default: return set_error("circuit blob: unknown op");
     }
     if (s.op == OP_GET) B2Z_REQUIRE(s.a < c->n_taps, "circuit blob: tap index out of range");
+    if (s.op == OP_GET_GLOBAL)  // operand a selects globals (0) / mix (1); the verifier and the generated kernel index both tables with b
+      B2Z_REQUIRE(s.a < 2 && s.b < (s.a == 0 ? c->globals_size : c->mix_size), "circuit blob: GetGlobal operand out of range");
   }
   B2Z_REQUIRE(c->ret < nm, "circuit blob: ret out of range");
+  {  // witness-generation program: base-field ops only, no forward references, operands in range
+    size_t nw = 0;
+    for (const auto& s : c->wit_steps) {
+      switch (s.op) {
+        case OP_CONST: break;
+        case OP_GET: B2Z_REQUIRE(s.a < c->n_taps && c->tap_group[s.a] != B2Z_GROUP_ACCUM, "circuit blob: witgen tap out of range"); break;
+        case OP_GET_GLOBAL: B2Z_REQUIRE(s.a == 0 && s.b < c->globals_size, "circuit blob: witgen GetGlobal operand out of range"); break;
+        case OP_ADD: case OP_SUB: case OP_MUL: B2Z_REQUIRE(s.a < nw && s.b < nw, "circuit blob: witgen forward reference"); break;
+        default: return set_error("circuit blob: op not allowed in the witgen program");
+      }
+      nw++;
+    }
+    for (size_t k = 0; k < c->wit_store_col.size(); k++)
+      B2Z_REQUIRE(c->wit_store_col[k] < c->group_size[2] && c->wit_store_var[k] < nw, "circuit blob: witgen store out of range");
+    for (uint32_t col : c->accum_col) B2Z_REQUIRE(col < c->group_size[2], "circuit blob: accumulator column out of range");
+    for (size_t k = 0; k < c->pin_col.size(); k++)
+      B2Z_REQUIRE(c->pin_col[k] < c->group_size[2] && c->pin_global[k] < c->globals_size, "circuit blob: pin out of range");
+  }
   c->max_exp = 0;
   for (uint32_t e : c->mix_exp) c->max_exp = std::max<size_t>(c->max_exp, e);
   return nullptr;
@@ -151,12 +176,7 @@ b2z_err circuit_parse(b2z_circuit* c, const uint32_t* blob, size_t words) {
 // Seal length (words) for a given po2 -- the layout of prove/write_iop.rs + merkle.rs + fri.rs.
 static void merkle_params(size_t rows, size_t& layers, size_t& top_size) {
   layers = ilog2(rows);
-  size_t top_layer = 0;
-  for (size_t i = 1; i < layers; i++) {
-    if (((size_t)1 << i) > B2Z_QUERIES) break;
-    top_layer = i;
-  }
-  top_size = (size_t)1 << top_layer;
+  top_size = (size_t)1 << pp_merkle_top_layer(layers, B2Z_QUERIES);  // [RECALL med] protocol_params.h
 }
 size_t circuit_seal_words(const b2z_circuit* c, unsigned po2) {
   size_t n = (size_t)1 << po2, domain = 4 * n;
@@ -180,6 +200,42 @@ size_t circuit_seal_words(const b2z_circuit* c, unsigned po2) {
   words += B2Z_QUERIES * per_query;
   return words;
 }
+
+// ---------------- NVRTC (dlopen'd) + cubin cache ----------------
+typedef struct _nvrtcProgram* nvrtcProgram;
+struct Nvrtc {
+  void* h = nullptr;
+  int (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+  int (*CompileProgram)(nvrtcProgram, int, const char* const*) = nullptr;
+  int (*GetCUBINSize)(nvrtcProgram, size_t*) = nullptr;
+  int (*GetCUBIN)(nvrtcProgram, char*) = nullptr;
+  int (*GetProgramLogSize)(nvrtcProgram, size_t*) = nullptr;
+  int (*GetProgramLog)(nvrtcProgram, char*) = nullptr;
+  int (*DestroyProgram)(nvrtcProgram*) = nullptr;
+  int (*Version)(int*, int*) = nullptr;
+  bool load() {
+    if (h) return true;
+    const char* names[] = {"libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so", "libnvrtc.so"};
+    for (const char* nme : names) {
+      h = dlopen(nme, RTLD_NOW | RTLD_LOCAL);
+      if (h) break;
+    }
+    if (!h) return false;
+#define LOADSYM(field, name) *(void**)(&field) = dlsym(h, name); if (!field) return false;
+    LOADSYM(CreateProgram, "nvrtcCreateProgram")
+    LOADSYM(CompileProgram, "nvrtcCompileProgram")
+    LOADSYM(GetCUBINSize, "nvrtcGetCUBINSize")
+    LOADSYM(GetCUBIN, "nvrtcGetCUBIN")
+    LOADSYM(GetProgramLogSize, "nvrtcGetProgramLogSize")
+    LOADSYM(GetProgramLog, "nvrtcGetProgramLog")
+    LOADSYM(DestroyProgram, "nvrtcDestroyProgram")
+    LOADSYM(Version, "nvrtcVersion")
+#undef LOADSYM
+    return true;
+  }
+};
+static Nvrtc g_nvrtc;
+
 
 // ---------------- code generation ----------------
 static const char* PRELUDE = R"CUDA(
@@ -600,41 +656,15 @@ void circuit_codegen(b2z_circuit* c) {
     h ^= ch;
     h *= 1099511628211ull;
   }
+  // the cubin cache key also covers the compiler that would produce the cubin (a cache filled by another NVRTC is not reused)
+  int vmaj = 0, vmin = 0;
+  if (g_nvrtc.load()) g_nvrtc.Version(&vmaj, &vmin);
+  for (unsigned char ch : {(unsigned char)vmaj, (unsigned char)vmin}) {
+    h ^= ch;
+    h *= 1099511628211ull;
+  }
   c->source_hash = h;
 }
-
-// ---------------- NVRTC (dlopen'd) + cubin cache ----------------
-typedef struct _nvrtcProgram* nvrtcProgram;
-struct Nvrtc {
-  void* h = nullptr;
-  int (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
-  int (*CompileProgram)(nvrtcProgram, int, const char* const*) = nullptr;
-  int (*GetCUBINSize)(nvrtcProgram, size_t*) = nullptr;
-  int (*GetCUBIN)(nvrtcProgram, char*) = nullptr;
-  int (*GetProgramLogSize)(nvrtcProgram, size_t*) = nullptr;
-  int (*GetProgramLog)(nvrtcProgram, char*) = nullptr;
-  int (*DestroyProgram)(nvrtcProgram*) = nullptr;
-  bool load() {
-    if (h) return true;
-    const char* names[] = {"libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so", "libnvrtc.so"};
-    for (const char* nme : names) {
-      h = dlopen(nme, RTLD_NOW | RTLD_LOCAL);
-      if (h) break;
-    }
-    if (!h) return false;
-#define LOADSYM(field, name) *(void**)(&field) = dlsym(h, name); if (!field) return false;
-    LOADSYM(CreateProgram, "nvrtcCreateProgram")
-    LOADSYM(CompileProgram, "nvrtcCompileProgram")
-    LOADSYM(GetCUBINSize, "nvrtcGetCUBINSize")
-    LOADSYM(GetCUBIN, "nvrtcGetCUBIN")
-    LOADSYM(GetProgramLogSize, "nvrtcGetProgramLogSize")
-    LOADSYM(GetProgramLog, "nvrtcGetProgramLog")
-    LOADSYM(DestroyProgram, "nvrtcDestroyProgram")
-#undef LOADSYM
-    return true;
-  }
-};
-static Nvrtc g_nvrtc;
 
 static std::string cache_dir() {
   if (const char* e = getenv("B2Z_KERNEL_CACHE")) return e;
@@ -648,11 +678,11 @@ static std::string cache_dir() {
   return "./kernel_cache";
 }
 
-b2z_err circuit_cubin(b2z_circuit* c, std::vector<char>& cubin) {
+b2z_err circuit_cubin(b2z_circuit* c, std::vector<char>& cubin, bool force_recompile) {
   char name[64];
   snprintf(name, sizeof name, "/circuit_%016llx.cubin", (unsigned long long)c->source_hash);
   std::string dir = cache_dir(), path = dir + name;
-  {
+  if (!force_recompile) {
     std::ifstream f(path, std::ios::binary);
     if (f) {
       cubin.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
@@ -679,11 +709,14 @@ b2z_err circuit_cubin(b2z_circuit* c, std::vector<char>& cubin) {
   g_nvrtc.GetCUBIN(prog, cubin.data());
   g_nvrtc.DestroyProgram(&prog);
   mkdir(dir.c_str(), 0755);
-  std::ofstream f(path + ".tmp", std::ios::binary);
-  if (f) {
-    f.write(cubin.data(), (std::streamsize)cubin.size());
-    f.close();
-    rename((path + ".tmp").c_str(), path.c_str());
+  // unique temporary (several ranks may fill a cold cache at once), fsync, then an atomic rename
+  std::string tmp = path + ".tmp.XXXXXX";
+  int fd = mkstemp(&tmp[0]);
+  if (fd >= 0) {
+    bool ok = write(fd, cubin.data(), cubin.size()) == (ssize_t)cubin.size() && fsync(fd) == 0;
+    close(fd);
+    if (ok) ok = rename(tmp.c_str(), path.c_str()) == 0;
+    if (!ok) unlink(tmp.c_str());
   }
   return nullptr;
 }
@@ -691,7 +724,13 @@ b2z_err circuit_cubin(b2z_circuit* c, std::vector<char>& cubin) {
 b2z_err circuit_compile(b2z_ctx* ctx, b2z_circuit* c) {
   std::vector<char> cubin;
   B2Z_TRY(circuit_cubin(c, cubin));
-  B2Z_CUDA(cudaLibraryLoadData(&c->library, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+  if (cudaLibraryLoadData(&c->library, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess) {
+    // a cached cubin that does not load (partial write of an older build, other toolkit) is thrown away and rebuilt once
+    cudaGetLastError();
+    c->library = nullptr;
+    B2Z_TRY(circuit_cubin(c, cubin, /*force_recompile=*/true));
+    B2Z_CUDA(cudaLibraryLoadData(&c->library, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+  }
   B2Z_CUDA(cudaLibraryGetKernel(&c->k_eval_check, c->library, "b2z_eval_check"));
   B2Z_CUDA(cudaLibraryGetKernel(&c->k_witgen, c->library, "b2z_witgen"));
   if (c->parts_mode) {

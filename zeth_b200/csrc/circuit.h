@@ -32,6 +32,9 @@ struct b2z_circuit {
   bool parts_mode = false;                    // eval_check split into __noinline__ parts; tables in module constants
   unsigned points_per_thread = 1;             // coset points per thread of the generated eval_check (parts mode, B2Z_EVALCHECK_POINTS)
   void *ccp_dev = nullptr, *ckc_dev = nullptr;  // device addresses of the module's __constant__ tables (parts mode)
+  // control roots (risc0: control IDs): expected Merkle root of the code group per po2, checked by the verifier
+  uint32_t control_root[32][8] = {};
+  bool has_control_root[32] = {};
   // device-resident tables
   int device = -1;
   uint32_t* accum_col_dev = nullptr;
@@ -42,7 +45,7 @@ namespace b2z {
 enum { OP_CONST = 0, OP_CONST_EXT, OP_GET, OP_GET_GLOBAL, OP_ADD, OP_SUB, OP_MUL, OP_TRUE, OP_AND_EQZ, OP_AND_COND };
 b2z_err circuit_parse(b2z_circuit* c, const uint32_t* blob, size_t words);
 void circuit_codegen(b2z_circuit* c);
-b2z_err circuit_cubin(b2z_circuit* c, std::vector<char>& cubin);  // cache lookup, else NVRTC
+b2z_err circuit_cubin(b2z_circuit* c, std::vector<char>& cubin, bool force_recompile = false);  // cache lookup, else NVRTC
 b2z_err circuit_compile(b2z_ctx* ctx, b2z_circuit* c);  // NVRTC (or cubin cache) -> cudaLibrary
 size_t circuit_seal_words(const b2z_circuit* c, unsigned po2);
 }  // namespace b2z

@@ -43,6 +43,10 @@ struct b2z_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;          // host->device witness uploads overlapped with compute (b2z_prove_segment)
   std::vector<cudaEvent_t> h2d_events;
+  // pinned staging ring for PAGEABLE host witnesses (b2z_prove_segment): slots of 16 MB, one drain event per slot
+  char* stage_ring = nullptr;
+  std::vector<cudaEvent_t> stage_events;
+  bool last_upload_staged = false;
   uint64_t launches = 0;
   // per-size device table, built lazily: 3^rev(j) for zk_shift (NTT twist tables live in kernels_ntt.cu's registry)
   uint32_t* pow3rev[b2z::MAX_PO2 + 1] = {};
@@ -87,6 +91,8 @@ b2z_err launch_poly_divide(b2z_ctx* ctx, uint32_t* ext_coeffs, size_t count, con
 b2z_err launch_sub_lowcoeffs(b2z_ctx* ctx, uint32_t* ext_coeffs, const uint32_t* sub_dev, size_t n_sub);
 b2z_err launch_accum(b2z_ctx* ctx, uint32_t* accum, const uint32_t* data, const uint32_t* accum_cols_dev, size_t n_accum,
                      const uint32_t* mix_dev, const uint32_t* noise_dev, unsigned po2, size_t zk_rows);
+b2z_err launch_scatter(b2z_ctx* ctx, uint32_t* into, const uint32_t* index, const uint32_t* offsets, const uint32_t* values, size_t count);
+b2z_err launch_prefix_products(b2z_ctx* ctx, uint32_t* ext_io, size_t n);
 // query gathering: writes rows + Merkle paths for all queries straight into the device seal image
 struct GatherTree {
   const uint32_t* matrix;

@@ -285,6 +285,9 @@ b2z_err launch_hash_rows(b2z_ctx* ctx, uint32_t* out, const uint32_t* matrix, si
 b2z_err launch_hash_rows_chunk(b2z_ctx* ctx, uint32_t* out, const uint32_t* matrix, size_t rows, size_t cols, bool carry_in, bool last) {
   if (rows == 0) return nullptr;
   B2Z_REQUIRE(last || (cols > 0 && cols % P2_RATE == 0), "hash_rows_chunk: a non-final chunk must be a positive multiple of 16 columns");
+  // overwrite-mode sponge: only the 8 capacity words are carried between chunks, so an EMPTY final chunk has nothing to
+  // squeeze from (the rate cells of the previous permutation are gone) -- reject instead of writing zero digests
+  B2Z_REQUIRE(!(carry_in && last && cols == 0), "hash_rows_chunk: the final chunk of a carried sponge must not be empty");
   const unsigned flags = (carry_in ? HASH_CARRY_IN : 0u) | (last ? HASH_LAST : 0u);
   B2Z_TRY(upload_consts(ctx));
   // B2Z_HASH_MIXED=0 forces the INT-only kernel; the mixed kernel needs enough rows to fill the persistent grid

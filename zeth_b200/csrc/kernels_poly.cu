@@ -623,4 +623,103 @@ b2z_err launch_gather_queries(b2z_ctx* ctx, uint32_t* seal_dev, const GatherTree
   return nullptr;
 }
 
+// ---------------- scatter / prefix_products (remaining trait Hal ops) ----------------
+// Hal::scatter(into, index, offsets, values) [RECALL lo-med]: CSR-style -- `index` holds count + 1 row starts; cycle c owns the
+// entries idx in [index[c], index[c+1]) and performs into[offsets[idx]] = values[idx] in that order (a later entry of
+// the same cycle overwrites an earlier one; upstream runs the cycles in parallel, so cross-cycle duplicates are a race
+// there as well).  One thread per cycle keeps exactly that order.
+__global__ void scatter_kernel(uint32_t* __restrict__ into, const uint32_t* __restrict__ index, const uint32_t* __restrict__ offsets,
+                               const uint32_t* __restrict__ values, size_t count) {
+  size_t cycle = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (cycle >= count) return;
+  for (uint32_t idx = index[cycle], end = index[cycle + 1]; idx < end; idx++) into[offsets[idx]] = values[idx];
+}
+b2z_err launch_scatter(b2z_ctx* ctx, uint32_t* into, const uint32_t* index, const uint32_t* offsets, const uint32_t* values, size_t count) {
+  if (!count) return nullptr;
+  scatter_kernel<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(into, index, offsets, values, count);
+  ctx->launches++;
+  B2Z_CUDA(cudaGetLastError());
+  return nullptr;
+}
+
+// Hal::prefix_products(io) [RECALL med]: in-place inclusive prefix product of an AoS ext array, io[i] = io[0] * ... * io[i].
+// Three launches: per-block inclusive scan (4 elements per thread, Hillis-Steele over the thread products in shared
+// memory), one CTA turning the block totals into exclusive carries, and the carry multiplication.
+constexpr unsigned PFX_THREADS = 256, PFX_PER_THREAD = 4, PFX_BLOCK = PFX_THREADS * PFX_PER_THREAD;
+__global__ void __launch_bounds__(PFX_THREADS) prefix_products_local_kernel(uint32_t* __restrict__ io, size_t n, uint32_t* __restrict__ block_tot) {
+  __shared__ Fp4 sh[PFX_THREADS];
+  const unsigned t = threadIdx.x;
+  const size_t base = (size_t)blockIdx.x * PFX_BLOCK + (size_t)t * PFX_PER_THREAD;
+  Fp4 v[PFX_PER_THREAD];
+  Fp4 run = fp4_one();
+#pragma unroll
+  for (unsigned k = 0; k < PFX_PER_THREAD; k++) {
+    v[k] = base + k < n ? ld_ext(io + 4 * (base + k)) : fp4_one();
+    run = fp4_mul(run, v[k]);
+    v[k] = run;  // inclusive within the thread
+  }
+  sh[t] = run;
+  __syncthreads();
+  for (unsigned d = 1; d < PFX_THREADS; d <<= 1) {  // inclusive scan of the thread products (left factor first: order kept)
+    Fp4 left = t >= d ? sh[t - d] : fp4_one();
+    __syncthreads();
+    if (t >= d) sh[t] = fp4_mul(left, sh[t]);
+    __syncthreads();
+  }
+  const Fp4 excl = t ? sh[t - 1] : fp4_one();
+#pragma unroll
+  for (unsigned k = 0; k < PFX_PER_THREAD; k++)
+    if (base + k < n) st_ext(io + 4 * (base + k), fp4_mul(excl, v[k]));
+  if (t == PFX_THREADS - 1) st_ext(block_tot + 4 * blockIdx.x, sh[t]);
+}
+// block totals -> exclusive carries (in place), one CTA, chunks of PFX_THREADS totals with a running carry
+__global__ void __launch_bounds__(PFX_THREADS) prefix_products_carry_kernel(uint32_t* __restrict__ block_tot, size_t nblocks) {
+  __shared__ Fp4 sh[PFX_THREADS];
+  __shared__ Fp4 carry;
+  const unsigned t = threadIdx.x;
+  if (t == 0) carry = fp4_one();
+  __syncthreads();
+  for (size_t b0 = 0; b0 < nblocks; b0 += PFX_THREADS) {
+    const Fp4 own = b0 + t < nblocks ? ld_ext(block_tot + 4 * (b0 + t)) : fp4_one();
+    sh[t] = own;
+    __syncthreads();
+    for (unsigned d = 1; d < PFX_THREADS; d <<= 1) {
+      Fp4 left = t >= d ? sh[t - d] : fp4_one();
+      __syncthreads();
+      if (t >= d) sh[t] = fp4_mul(left, sh[t]);
+      __syncthreads();
+    }
+    const Fp4 c0 = carry;
+    const Fp4 excl = fp4_mul(c0, t ? sh[t - 1] : fp4_one());
+    if (b0 + t < nblocks) st_ext(block_tot + 4 * (b0 + t), excl);
+    __syncthreads();
+    if (t == PFX_THREADS - 1) carry = fp4_mul(c0, sh[t]);
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(PFX_THREADS) prefix_products_apply_kernel(uint32_t* __restrict__ io, size_t n, const uint32_t* __restrict__ carries) {
+  if (blockIdx.x == 0) return;  // carry of the first block is one
+  const Fp4 c = ld_ext(carries + 4 * blockIdx.x);
+  const size_t base = (size_t)blockIdx.x * PFX_BLOCK + (size_t)threadIdx.x * PFX_PER_THREAD;
+#pragma unroll
+  for (unsigned k = 0; k < PFX_PER_THREAD; k++)
+    if (base + k < n) st_ext(io + 4 * (base + k), fp4_mul(c, ld_ext(io + 4 * (base + k))));
+}
+b2z_err launch_prefix_products(b2z_ctx* ctx, uint32_t* io, size_t n) {
+  if (n <= 1) return nullptr;
+  const size_t nblocks = (n + PFX_BLOCK - 1) / PFX_BLOCK;
+  uint32_t* tot = nullptr;
+  B2Z_CUDA(cudaMallocAsync(&tot, 16 * nblocks, ctx->stream));
+  prefix_products_local_kernel<<<(unsigned)nblocks, PFX_THREADS, 0, ctx->stream>>>(io, n, tot);
+  ctx->launches++;
+  if (nblocks > 1) {
+    prefix_products_carry_kernel<<<1, PFX_THREADS, 0, ctx->stream>>>(tot, nblocks);
+    prefix_products_apply_kernel<<<(unsigned)nblocks, PFX_THREADS, 0, ctx->stream>>>(io, n, tot);
+    ctx->launches += 2;
+  }
+  B2Z_CUDA(cudaGetLastError());
+  B2Z_CUDA(cudaFreeAsync(tot, ctx->stream));
+  return nullptr;
+}
+
 }  // namespace b2z

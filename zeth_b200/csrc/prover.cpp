@@ -10,8 +10,12 @@
 //     query positions depend only on the transcript state, not on the opened data.
 #include <nvtx3/nvToolsExt.h>  // header-only; ranges show up in Nsight tools, no-ops otherwise
 
+#include <atomic>
+#include <condition_variable>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <thread>
 
 #include "circuit.h"
 #include "common.h"
@@ -80,12 +84,7 @@ struct MerkleParams {
   size_t rows, cols, layers, top_size;
   MerkleParams(size_t r, size_t c) : rows(r), cols(c) {
     layers = ilog2(r);
-    size_t top_layer = 0;
-    for (size_t i = 1; i < layers; i++) {
-      if (((size_t)1 << i) > B2Z_QUERIES) break;
-      top_layer = i;
-    }
-    top_size = (size_t)1 << top_layer;
+    top_size = (size_t)1 << pp_merkle_top_layer(layers, B2Z_QUERIES);  // [RECALL med] rule lives in protocol_params.h
   }
   size_t path_words() const { return 8 * (layers - ilog2(top_size)); }
 };
@@ -173,17 +172,23 @@ static b2z_err poly_group_finish(b2z_ctx* ctx, DevMem& mem, PolyGroupDev& pg, un
 // consumes each chunk as soon as its event fires: iNTT, LDE and -- when the chunk is a whole number of sponge blocks --
 // the leaf hashing of its columns (launch_hash_rows_chunk carries the sponge capacity in the leaf slots), so the
 // upload of chunk k+1 hides behind all the work on chunk k and only the interior Merkle layers remain at the end.
+struct UploadGate;  // host-side "this event has been recorded" latch (pageable sources are staged by helper threads)
 struct WitnessReady {
   cudaEvent_t noise = nullptr;
   std::vector<cudaEvent_t> code_chunks;  // one event per `code_chunk_cols` code columns (small: the first compute starts early)
   std::vector<cudaEvent_t> data_chunks;  // one event per `chunk_cols` data columns
   size_t chunk_cols = 0, code_chunk_cols = 0;
+  // cudaStreamWaitEvent on an event that has not been recorded yet is a no-op, so when the copies are issued by the staging
+  // threads the compute thread first blocks (on the host) until the chunk's event exists.  gate == nullptr: all recorded.
+  UploadGate* gate = nullptr;
+  size_t code_gate0 = 0, data_gate0 = 0, noise_gate = 0;  // gate indices of code chunk 0, data chunk 0 and the noise block
 };
+b2z_err upload_gate_wait(UploadGate* g, size_t idx);
 
 // prover.rs make_coeffs + commit_group (PolyGroup::new inlined so that the per-chunk work can start early)
 static b2z_err commit_group(b2z_ctx* ctx, DevMem& mem, PolyGroupDev& pg, const uint32_t* witness, size_t count, unsigned po2, Seal& seal,
                             HostRng& rng, const std::vector<cudaEvent_t>* chunk_events = nullptr, size_t chunk_cols = 0,
-                            cudaEvent_t whole_event = nullptr) {
+                            cudaEvent_t whole_event = nullptr, UploadGate* gate = nullptr, size_t gate0 = 0) {
   size_t n = (size_t)1 << po2, domain = 4 * n;
   uint32_t* coeffs = nullptr;
   B2Z_TRY(mem.alloc(&coeffs, count * n));
@@ -197,7 +202,10 @@ static b2z_err commit_group(b2z_ctx* ctx, DevMem& mem, PolyGroupDev& pg, const u
   if (hash_chunks) B2Z_TRY(mem.alloc(&pg.nodes, 2 * domain * 8));
   for (size_t c0 = 0, k = 0; c0 < count; c0 += chunk_cols, k++) {
     size_t cols = count - c0 < chunk_cols ? count - c0 : chunk_cols;
-    if (chunk_events && k < chunk_events->size()) B2Z_CUDA(cudaStreamWaitEvent(ctx->stream, (*chunk_events)[k], 0));
+    if (chunk_events && k < chunk_events->size()) {
+      if (gate) B2Z_TRY(upload_gate_wait(gate, gate0 + k));
+      B2Z_CUDA(cudaStreamWaitEvent(ctx->stream, (*chunk_events)[k], 0));
+    }
     // the first inverse pass reads the witness directly and writes the coefficient buffer (no separate copy)
     B2Z_TRY(launch_interpolate(ctx, coeffs + c0 * n, cols, po2, /*fuse_zk_shift=*/true, witness + c0 * n));
     B2Z_TRY(launch_evaluate(ctx, pg.evaluated + c0 * domain, coeffs + c0 * n, cols, po2 + 2, 2));
@@ -246,17 +254,18 @@ b2z_err prove_segment_device(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, c
   const size_t wa = c->group_size[0], wc = c->group_size[1], wd = c->group_size[2];
   const size_t gsz = c->globals_size, msz = c->mix_size;
   const size_t seal_words = circuit_seal_words(c, po2);
-  B2Z_TRY(ensure_pinned(ctx, seal_words + 64 + 4 * (c->n_taps + 64)));
+  B2Z_TRY(ensure_pinned(ctx, seal_words + 64 + 4 * (c->n_taps + 64) + 4 * (c->tot_combo_backs + 8)));
   Seal seal{ctx->pinned, 0, seal_words};
-  uint32_t* scratch = ctx->pinned + seal_words + 8;  // [root(8)] [eval_u ...]
+  uint32_t* scratch = ctx->pinned + seal_words + 8;  // [root(8)] [eval_u ...] [DEEP remainders]
+  uint32_t* rem_host = ctx->pinned + seal_words + 64 + 4 * (c->n_taps + 64);
+  size_t n_rem = 0;
   DevMem mem(ctx);
   PhaseTimer tm(ctx);
   HostRng rng;
   uint32_t dg[8];
   tm.begin(10);
 
-  static const uint8_t PROOF_SYSTEM_INFO[16] = {'R', 'I', 'S', 'C', '0', '_', 'S', 'T', 'A', 'R', 'K', ':', 'v', '1', '_', '_'};
-  hash_info(PROOF_SYSTEM_INFO, dg);
+  hash_info(reinterpret_cast<const uint8_t*>(PP_PROOF_SYSTEM_INFO), dg);  // [RECALL med] protocol_params.h
   rng.mix(dg);
   hash_info(c->info, dg);
   rng.mix(dg);
@@ -273,11 +282,11 @@ b2z_err prove_segment_device(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, c
   PolyGroupDev pg[3], check_pg;
   tm.begin(0);
   B2Z_TRY(commit_group(ctx, mem, pg[B2Z_GROUP_CODE], code_dev, wc, po2, seal, rng, ready ? &ready->code_chunks : nullptr,
-                       ready ? ready->code_chunk_cols : 0));
+                       ready ? ready->code_chunk_cols : 0, nullptr, ready ? ready->gate : nullptr, ready ? ready->code_gate0 : 0));
   tm.end(0);
   tm.begin(1);
   B2Z_TRY(commit_group(ctx, mem, pg[B2Z_GROUP_DATA], data_dev, wd, po2, seal, rng, ready ? &ready->data_chunks : nullptr,
-                       ready ? ready->chunk_cols : 0));
+                       ready ? ready->chunk_cols : 0, nullptr, ready ? ready->gate : nullptr, ready ? ready->data_gate0 : 0));
   tm.end(1);
 
   std::vector<uint32_t> mix_host(msz + 1);
@@ -288,7 +297,10 @@ b2z_err prove_segment_device(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, c
   tm.begin(2);
   uint32_t* accum = nullptr;
   B2Z_TRY(mem.alloc(&accum, wa * n));
-  if (ready && ready->noise) B2Z_CUDA(cudaStreamWaitEvent(ctx->stream, ready->noise, 0));
+  if (ready && ready->noise) {
+    if (ready->gate) B2Z_TRY(upload_gate_wait(ready->gate, ready->noise_gate));
+    B2Z_CUDA(cudaStreamWaitEvent(ctx->stream, ready->noise, 0));
+  }
   B2Z_TRY(launch_accum(ctx, accum, data_dev, c->accum_col_dev, c->accum_col.size(), mix_dev, accum_noise_dev, po2, zk_rows));
   tm.end(2);
   tm.begin(3);
@@ -419,7 +431,19 @@ b2z_err prove_segment_device(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, c
     }
     B2Z_TRY(launch_sub_lowcoeffs(ctx, combos + 4 * n_combos * n, cu_dev + 4 * c->tot_combo_backs, 1));
     B2Z_TRY(launch_poly_divide(ctx, combos + 4 * n_combos * n, n, z_pow, rem_dev + 4 * nrem++));
+    // every division must be exact (prover.rs asserts a zero remainder): the remainders come back with the next transcript
+    // round trip and an unsatisfied witness fails the segment instead of yielding a garbage seal
+    n_rem = nrem;
+    B2Z_CUDA(cudaMemcpyAsync(rem_host, rem_dev, 16 * n_rem, cudaMemcpyDeviceToHost, ctx->stream));
   }
+  auto check_remainders = [&]() -> b2z_err {
+    for (size_t i = 0; i < 4 * n_rem; i++)
+      if (rem_host[i] != 0)
+        return set_error("witness does not satisfy the circuit: non-zero remainder in DEEP division " + std::to_string(i / 4) +
+                         " (constraint violated, or code/data/accum columns inconsistent with the transcript)");
+    n_rem = 0;
+    return nullptr;
+  };
   uint32_t* final_coeffs = nullptr;
   B2Z_TRY(mem.alloc(&final_coeffs, 4 * n));
   B2Z_TRY(launch_sum_extelem(ctx, final_coeffs, combos, n, n_combos + 1));
@@ -448,6 +472,7 @@ b2z_err prove_segment_device(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, c
     B2Z_CUDA(cudaMemcpyAsync(seal.w + seal.pos, r.nodes + 8 * mp.top_size, 32 * mp.top_size, cudaMemcpyDeviceToHost, ctx->stream));
     B2Z_CUDA(cudaMemcpyAsync(scratch, r.nodes + 8, 32, cudaMemcpyDeviceToHost, ctx->stream));
     B2Z_CUDA(cudaStreamSynchronize(ctx->stream));
+    B2Z_TRY(check_remainders());
     seal.pos += 8 * mp.top_size;
     rng.mix(scratch);
     Fp4 fold_mix = rng.random_ext();
@@ -466,6 +491,7 @@ b2z_err prove_segment_device(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, c
     B2Z_REQUIRE(seal.pos + 4 * size <= seal.cap, "seal overflow");
     B2Z_CUDA(cudaMemcpyAsync(seal.w + seal.pos, fin, 16 * size, cudaMemcpyDeviceToHost, ctx->stream));
     B2Z_CUDA(cudaStreamSynchronize(ctx->stream));
+    B2Z_TRY(check_remainders());
     host_hash_elem_slice(seal.w + seal.pos, 4 * size, dg);
     seal.pos += 4 * size;
     rng.mix(dg);
@@ -485,7 +511,10 @@ b2z_err prove_segment_device(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, c
       trees.push_back(t);
       off += cols + mp.path_words();
     };
-    for (int g = 0; g < 3; g++) add_tree(pg[g].evaluated, pg[g].nodes, domain, pg[g].count);
+    for (int k = 0; k < 3; k++) {  // [RECALL med] opening order: protocol_params.h PP_QUERY_ORDER
+      const int g = PP_QUERY_ORDER[k];
+      add_tree(pg[g].evaluated, pg[g].nodes, domain, pg[g].count);
+    }
     add_tree(check_pg.evaluated, check_pg.nodes, domain, B2Z_CHECK_SIZE);
     for (auto& r : rounds) add_tree(r.evaluated, r.nodes, r.domain / B2Z_FRI_FOLD, 64);
     size_t record_words = off;
@@ -519,13 +548,97 @@ b2z_err prove_segment_device(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, c
 }
 
 
-// Host buffers in, seal out.  The witness is uploaded on the copy stream in column chunks while the compute stream is
-// already committing the code group and the first data chunks (pinned host memory makes the copies truly asynchronous).
+// ---- host-buffer entry point: witness upload overlapped with the commits ----
+// The witness crosses PCIe on ctx->copy_stream in column chunks, each followed by an event the compute stream waits on.
+//   * pinned sources (cudaMallocHost / cudaHostRegister memory): the copies are truly asynchronous, the calling thread
+//     enqueues all of them up front;
+//   * pageable sources (a Rust Vec<u32>, a numpy array): cudaMemcpyAsync would stage them synchronously on the calling
+//     thread and serialise the 3.5 GB upload with the compute, so STAGE_THREADS helper threads memcpy 16 MB pieces into a
+//     pinned ring (2 slots per thread, owned by the context) and issue the device copies from there; the compute thread
+//     blocks on a host-side latch until a chunk's event has been recorded.  Needs ~15 GB/s of host memcpy to stay hidden.
+struct UploadGate {
+  std::mutex m;
+  std::condition_variable cv;
+  std::vector<char> recorded;
+  b2z_err error = nullptr;
+  std::string error_text;
+};
+b2z_err upload_gate_wait(UploadGate* g, size_t idx) {
+  std::unique_lock<std::mutex> lock(g->m);
+  g->cv.wait(lock, [&] { return g->recorded[idx] || g->error; });
+  return g->error ? set_error(g->error_text) : nullptr;
+}
+
+namespace {
+constexpr size_t STAGE_THREADS = 4, STAGE_SLOTS = 2 * STAGE_THREADS, STAGE_PIECE_BYTES = (size_t)16 << 20;
+
+struct UploadChunk {  // one event's worth of bytes
+  char* dst;
+  const char* src;
+  size_t bytes;
+  cudaEvent_t event;
+  size_t first_piece = 0, n_pieces = 0;
+  std::atomic<size_t> issued{0};
+  UploadChunk(char* d, const char* s, size_t b, cudaEvent_t e) : dst(d), src(s), bytes(b), event(e) {}
+  UploadChunk(const UploadChunk& o) : dst(o.dst), src(o.src), bytes(o.bytes), event(o.event), first_piece(o.first_piece), n_pieces(o.n_pieces) {}
+};
+
+bool host_pointer_is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+void staged_upload_worker(b2z_ctx* ctx, std::vector<UploadChunk>* chunks, std::atomic<size_t>* next_piece, size_t total_pieces, size_t tid,
+                          UploadGate* gate) {
+  cudaSetDevice(ctx->device);
+  auto fail = [&](cudaError_t e) {
+    std::lock_guard<std::mutex> lock(gate->m);
+    if (!gate->error) {
+      gate->error_text = std::string("staged witness upload: ") + cudaGetErrorString(e);
+      gate->error = gate->error_text.c_str();
+    }
+    gate->cv.notify_all();
+  };
+  size_t use = 0;
+  for (;;) {
+    size_t p = next_piece->fetch_add(1);
+    if (p >= total_pieces) return;
+    // chunk of piece p (chunks are few: linear scan)
+    size_t k = 0;
+    while (k + 1 < chunks->size() && (*chunks)[k + 1].first_piece <= p) k++;
+    UploadChunk& ch = (*chunks)[k];
+    size_t off = (p - ch.first_piece) * STAGE_PIECE_BYTES;
+    size_t len = ch.bytes - off < STAGE_PIECE_BYTES ? ch.bytes - off : STAGE_PIECE_BYTES;
+    size_t slot = 2 * tid + (use++ & 1);
+    cudaError_t e = cudaEventSynchronize(ctx->stage_events[slot]);  // the slot's previous device copy has drained
+    if (e != cudaSuccess) return fail(e);
+    char* ring = ctx->stage_ring + slot * STAGE_PIECE_BYTES;
+    memcpy(ring, ch.src + off, len);
+    e = cudaMemcpyAsync(ch.dst + off, ring, len, cudaMemcpyHostToDevice, ctx->copy_stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->stage_events[slot], ctx->copy_stream);
+    if (e != cudaSuccess) return fail(e);
+    // the thread that issues a chunk's last piece records the chunk event: every earlier piece is already in the stream
+    if (ch.issued.fetch_add(1) + 1 == ch.n_pieces) {
+      e = cudaEventRecord(ch.event, ctx->copy_stream);
+      if (e != cudaSuccess) return fail(e);
+      std::lock_guard<std::mutex> lock(gate->m);
+      gate->recorded[k] = 1;
+      gate->cv.notify_all();
+    }
+  }
+}
+}  // namespace
+
 b2z_err prove_segment_host(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, const uint32_t* code_host, const uint32_t* data_host,
                            const uint32_t* globals_host, const uint32_t* accum_noise_host, size_t zk_rows, uint32_t* seal_host,
                            size_t* seal_words) {
   B2Z_REQUIRE(po2 >= 1 && po2 <= 24, "po2 out of range");
   const size_t n = (size_t)1 << po2;
+  B2Z_REQUIRE(zk_rows < n, "zk_rows must be smaller than the trace");
   const size_t wa = c->group_size[0], wc = c->group_size[1], wd = c->group_size[2];
   if (!ctx->copy_stream) B2Z_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   WitnessReady ready;
@@ -538,35 +651,91 @@ b2z_err prove_segment_host(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, con
     B2Z_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     ctx->h2d_events.push_back(e);
   }
+  DevMem wit(ctx);  // released on every exit path
   uint32_t *code = nullptr, *data = nullptr, *noise = nullptr;
-  B2Z_CUDA(cudaMallocAsync(&code, 4 * (wc * n + 1), ctx->stream));
-  B2Z_CUDA(cudaMallocAsync(&data, 4 * (wd * n + 1), ctx->stream));
-  B2Z_CUDA(cudaMallocAsync(&noise, 4 * (wa * zk_rows + 1), ctx->stream));
+  B2Z_TRY(wit.alloc(&code, wc * n + 1));
+  B2Z_TRY(wit.alloc(&data, wd * n + 1));
+  B2Z_TRY(wit.alloc(&noise, wa * zk_rows + 1));
   // the copy stream may only touch the buffers once the (stream-ordered) allocations are visible
   cudaEvent_t alloc_done = ctx->h2d_events[nchunks + ncode + 1];
   B2Z_CUDA(cudaEventRecord(alloc_done, ctx->stream));
   B2Z_CUDA(cudaStreamWaitEvent(ctx->copy_stream, alloc_done, 0));
+  // upload plan in consumption order: code chunks, data chunks, accum noise
+  std::vector<UploadChunk> chunks;
   for (size_t k = 0; k < ncode; k++) {
     size_t c0 = k * ready.code_chunk_cols, cols = wc - c0 < ready.code_chunk_cols ? wc - c0 : ready.code_chunk_cols;
-    B2Z_CUDA(cudaMemcpyAsync(code + c0 * n, code_host + c0 * n, 4 * cols * n, cudaMemcpyHostToDevice, ctx->copy_stream));
-    B2Z_CUDA(cudaEventRecord(ctx->h2d_events[nchunks + k], ctx->copy_stream));
+    chunks.emplace_back((char*)(code + c0 * n), (const char*)(code_host + c0 * n), 4 * cols * n, ctx->h2d_events[nchunks + k]);
     ready.code_chunks.push_back(ctx->h2d_events[nchunks + k]);
   }
   for (size_t k = 0; k < nchunks; k++) {
     size_t c0 = k * ready.chunk_cols, cols = wd - c0 < ready.chunk_cols ? wd - c0 : ready.chunk_cols;
-    B2Z_CUDA(cudaMemcpyAsync(data + c0 * n, data_host + c0 * n, 4 * cols * n, cudaMemcpyHostToDevice, ctx->copy_stream));
-    B2Z_CUDA(cudaEventRecord(ctx->h2d_events[k], ctx->copy_stream));
+    chunks.emplace_back((char*)(data + c0 * n), (const char*)(data_host + c0 * n), 4 * cols * n, ctx->h2d_events[k]);
     ready.data_chunks.push_back(ctx->h2d_events[k]);
   }
-  B2Z_CUDA(cudaMemcpyAsync(noise, accum_noise_host, 4 * wa * zk_rows, cudaMemcpyHostToDevice, ctx->copy_stream));
   ready.noise = ctx->h2d_events[nchunks + ncode];
-  B2Z_CUDA(cudaEventRecord(ready.noise, ctx->copy_stream));
+  chunks.emplace_back((char*)noise, (const char*)accum_noise_host, 4 * wa * zk_rows, ready.noise);
+  ready.code_gate0 = 0;
+  ready.data_gate0 = ncode;
+  ready.noise_gate = ncode + nchunks;
+
+  const bool pinned = (wc == 0 || host_pointer_is_pinned(code_host)) && (wd == 0 || host_pointer_is_pinned(data_host)) &&
+                      (wa * zk_rows == 0 || host_pointer_is_pinned(accum_noise_host));
+  ctx->last_upload_staged = !pinned;
+  if (pinned) {
+    for (auto& ch : chunks) {
+      if (ch.bytes) B2Z_CUDA(cudaMemcpyAsync(ch.dst, ch.src, ch.bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+      B2Z_CUDA(cudaEventRecord(ch.event, ctx->copy_stream));
+    }
+    b2z_err err = prove_segment_device(ctx, c, po2, code, data, globals_host, noise, zk_rows, seal_host, seal_words, &ready);
+    cudaStreamSynchronize(ctx->copy_stream);
+    return err;
+  }
+  // pageable sources: staged through the pinned ring by helper threads
+  if (!ctx->stage_ring) {
+    B2Z_CUDA(cudaMallocHost((void**)&ctx->stage_ring, STAGE_SLOTS * STAGE_PIECE_BYTES));
+    for (size_t i = 0; i < STAGE_SLOTS; i++) {
+      cudaEvent_t e;
+      B2Z_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      ctx->stage_events.push_back(e);
+    }
+  }
+  size_t total_pieces = 0;
+  for (auto& ch : chunks) {
+    ch.first_piece = total_pieces;
+    ch.n_pieces = (ch.bytes + STAGE_PIECE_BYTES - 1) / STAGE_PIECE_BYTES;
+    if (ch.n_pieces == 0) ch.n_pieces = 1;  // an empty chunk still records its event (zero-byte piece)
+    total_pieces += ch.n_pieces;
+  }
+  UploadGate gate;
+  gate.recorded.assign(chunks.size(), 0);
+  ready.gate = &gate;
+  std::atomic<size_t> next_piece{0};
+  std::vector<std::thread> workers;
+  for (size_t t = 0; t < STAGE_THREADS; t++) workers.emplace_back(staged_upload_worker, ctx, &chunks, &next_piece, total_pieces, t, &gate);
   b2z_err err = prove_segment_device(ctx, c, po2, code, data, globals_host, noise, zk_rows, seal_host, seal_words, &ready);
+  if (err) next_piece.store(total_pieces);  // stop issuing pieces; the workers drain and exit
+  for (auto& w : workers) w.join();
   cudaStreamSynchronize(ctx->copy_stream);
-  cudaFreeAsync(code, ctx->stream);
-  cudaFreeAsync(data, ctx->stream);
-  cudaFreeAsync(noise, ctx->stream);
   return err;
+}
+
+// Control root of a code group (risc0: the control ID of a po2): the Merkle root its commitment has in every honest seal.
+// Same commit sequence as the prover's code group (iNTT, zk_shift, x4 LDE, Poseidon2 tree); the root is what
+// b2z_verify_segment compares the seal's code root with.
+b2z_err compute_control_root(b2z_ctx* ctx, unsigned po2, const uint32_t* code_dev, size_t cols, uint32_t* root_host) {
+  B2Z_REQUIRE(po2 >= 1 && po2 <= 24 && cols > 0, "control root: bad arguments");
+  const size_t n = (size_t)1 << po2, domain = 4 * n;
+  DevMem mem(ctx);
+  uint32_t *coeffs = nullptr, *evaluated = nullptr, *nodes = nullptr;
+  B2Z_TRY(mem.alloc(&coeffs, cols * n));
+  B2Z_TRY(mem.alloc(&evaluated, cols * domain));
+  B2Z_TRY(mem.alloc(&nodes, 2 * domain * 8));
+  B2Z_TRY(launch_interpolate(ctx, coeffs, cols, po2, /*fuse_zk_shift=*/true, code_dev));
+  B2Z_TRY(launch_evaluate(ctx, evaluated, coeffs, cols, po2 + 2, 2));
+  B2Z_TRY(merkle_build(ctx, nodes, evaluated, domain, cols));
+  B2Z_CUDA(cudaMemcpyAsync(root_host, nodes + 8, 32, cudaMemcpyDeviceToHost, ctx->stream));
+  B2Z_CUDA(cudaStreamSynchronize(ctx->stream));
+  return nullptr;
 }
 
 }  // namespace b2z

@@ -101,7 +101,7 @@ Fp4 HostRng::random_ext() {
 }
 uint32_t HostRng::random_bits(unsigned bits) {
   uint32_t val = fp_to_u32(random_elem());
-  for (int i = 0; i < 3; i++) {
+  for (int i = 0; i < PP_RANDOM_BITS_EXTRA_DRAWS; i++) {  // [RECALL lo-med] protocol_params.h
     uint32_t nv = fp_to_u32(random_elem());
     if (val == 0) val = nv;
   }

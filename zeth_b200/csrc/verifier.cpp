@@ -29,15 +29,12 @@ struct MerkleVerifier {
   bool init(ReadIop& iop, size_t r, size_t c) {
     rows = r;
     cols = c;
-    size_t layers = ilog2(r), top_layer = 0;
-    for (size_t i = 1; i < layers; i++) {
-      if (((size_t)1 << i) > B2Z_QUERIES) break;
-      top_layer = i;
-    }
-    top_size = (size_t)1 << top_layer;
+    top_size = (size_t)1 << pp_merkle_top_layer(ilog2(r), B2Z_QUERIES);  // [RECALL med] protocol_params.h
     top.assign(2 * top_size * 8, 0);
     const uint32_t* p = iop.read(8 * top_size);
     if (!p) return false;
+    for (size_t i = 0; i < 8 * top_size; i++)
+      if (p[i] >= P) return false;  // upstream's hash_pair asserts reduced digest words: x + P would hash like x (malleability)
     memcpy(&top[8 * top_size], p, 32 * top_size);
     for (size_t i = top_size; i-- > 1;) host_hash_pair(&top[8 * 2 * i], &top[8 * (2 * i + 1)], &top[8 * i]);
     iop.rng.mix(&top[8]);
@@ -57,6 +54,8 @@ struct MerkleVerifier {
       size_t low = idx & 1;
       const uint32_t* other = iop.read(8);
       if (!other) return nullptr;
+      for (int i = 0; i < 8; i++)
+        if (other[i] >= P) return nullptr;  // non-canonical sibling digest
       idx /= 2;
       if (low) host_hash_pair(other, cur, tmp);
       else host_hash_pair(cur, other, tmp);
@@ -143,9 +142,8 @@ int verify_segment(const b2z_circuit* c, const uint32_t* seal, size_t seal_words
   ReadIop iop{seal, seal_words};
   const size_t wa = c->group_size[0], wc = c->group_size[1], wd = c->group_size[2];
   const size_t gsz = c->globals_size, msz = c->mix_size;
-  static const uint8_t PROOF_SYSTEM_INFO[16] = {'R', 'I', 'S', 'C', '0', '_', 'S', 'T', 'A', 'R', 'K', ':', 'v', '1', '_', '_'};
   uint32_t dg[8];
-  hash_info(PROOF_SYSTEM_INFO, dg);
+  hash_info(reinterpret_cast<const uint8_t*>(PP_PROOF_SYSTEM_INFO), dg);  // [RECALL med] protocol_params.h
   iop.rng.mix(dg);
   hash_info(c->info, dg);
   iop.rng.mix(dg);
@@ -161,6 +159,12 @@ int verify_segment(const b2z_circuit* c, const uint32_t* seal, size_t seal_words
   const size_t n = (size_t)1 << po2, domain = 4 * n;
   MerkleVerifier mv[3], mcheck;
   if (!mv[B2Z_GROUP_CODE].init(iop, domain, wc)) return 4;
+  {
+    // verify/mod.rs check_code(po2, code_merkle.root()): the seal must commit to THIS program's code columns (the
+    // control-ID check behind receipt.verify(image_id)).  Fail closed when no control root is registered for the po2.
+    if (po2 >= 32 || !c->has_control_root[po2]) return 15;
+    if (memcmp(c->control_root[po2], &mv[B2Z_GROUP_CODE].top[8], 32) != 0) return 14;
+  }
   if (!mv[B2Z_GROUP_DATA].init(iop, domain, wd)) return 4;
   std::vector<uint32_t> mix(msz + 1);
   for (size_t i = 0; i < msz; i++) mix[i] = iop.rng.random_elem();
@@ -185,7 +189,7 @@ int verify_segment(const b2z_circuit* c, const uint32_t* seal, size_t seal_words
     }
   Fp4 result = poly_ext(c, poly_mix, eval_u.data(), globals, mix.data());
   {
-    static const int remap[4] = {0, 2, 1, 3};
+    const int* remap = PP_CHECK_REMAP;  // [RECALL med] protocol_params.h
     Fp4 check = fp4_zero();
     for (int i = 0; i < 4; i++) {
       Fp4 zi = fp4_pow(z, (uint64_t)i);
@@ -252,7 +256,8 @@ int verify_segment(const b2z_circuit* c, const uint32_t* seal, size_t seal_words
     size_t pos = iop.rng.random_bits(ilog2(domain));
     Fp4 x = fp4_from_fp(fp_pow(gen0, pos));
     const uint32_t* rows[3];
-    for (int g = 0; g < 3; g++) {
+    for (int k = 0; k < 3; k++) {  // [RECALL med] opening order: protocol_params.h PP_QUERY_ORDER
+      const int g = PP_QUERY_ORDER[k];
       rows[g] = mv[g].verify(iop, pos);
       if (!rows[g]) return 9;
     }

@@ -34,6 +34,9 @@ _ERR_FUNCS = [
     "b2z_mix_poly_coeffs", "b2z_eltwise_add_elem", "b2z_eltwise_sum_extelem", "b2z_eltwise_copy_elem",
     "b2z_eltwise_zeroize_elem", "b2z_gather_sample", "b2z_poly_divide", "b2z_circuit_load", "b2z_circuit_precompile",
     "b2z_circuit_free", "b2z_eval_check", "b2z_accumulate", "b2z_witgen", "b2z_prove_segment_device", "b2z_prove_segment",
+    "b2z_scatter", "b2z_prefix_products", "b2z_compute_control_root", "b2z_circuit_set_control_root",
+    "b2z_session_create", "b2z_session_destroy", "b2z_session_set_control_root", "b2z_prove_session",
+    "b2z_receipt_assemble", "b2z_receipt_free", "b2z_receipt_serialize", "b2z_receipt_deserialize",
 ]
 
 
@@ -56,6 +59,24 @@ def load_library():
     L.b2z_circuit_source.restype = C.c_char_p
     L.b2z_phase_name.restype = C.c_char_p
     L.b2z_phase_name.argtypes = [C.c_size_t]
+    L.b2z_verify_segment.restype = C.c_int
+    L.b2z_verify_receipt.restype = C.c_int
+    L.b2z_circuit_get_control_root.restype = C.c_int
+    L.b2z_session_circuit.restype = C.c_void_p
+    L.b2z_session_circuit.argtypes = [C.c_void_p]
+    L.b2z_session_context.restype = C.c_void_p
+    L.b2z_session_context.argtypes = [C.c_void_p, C.c_uint]
+    L.b2z_session_in_flight.restype = C.c_uint
+    L.b2z_session_in_flight.argtypes = [C.c_void_p]
+    L.b2z_session_launch_count.restype = C.c_uint64
+    L.b2z_session_launch_count.argtypes = [C.c_void_p]
+    L.b2z_session_last_wall_ms.restype = C.c_double
+    L.b2z_session_last_wall_ms.argtypes = [C.c_void_p]
+    L.b2z_session_last_retries.restype = C.c_size_t
+    L.b2z_session_last_retries.argtypes = [C.c_void_p]
+    L.b2z_session_last_segment_ms.restype = C.c_size_t
+    L.b2z_bytes_free.restype = None
+    L.b2z_bytes_free.argtypes = [C.c_void_p]
     _LIB = L
     return L
 
@@ -100,11 +121,28 @@ class Circuit:
             self.h = C.c_void_p()
 
     def verify(self, seal) -> int:
-        """Host-side STARK verifier (receipt.verify for one segment): 0 = accepted, else a rejection code."""
+        """Host-side STARK verifier (receipt.verify for one segment): 0 = accepted, else a rejection code
+        (14: code root != registered control root, 15: no control root registered for the seal's po2)."""
         s = _u32(seal)
         L = load_library()
-        L.b2z_verify_segment.restype = C.c_int
         return int(L.b2z_verify_segment(self.h, _vp(s), C.c_size_t(s.size)))
+
+    def set_control_root(self, po2: int, root):
+        """Register the expected Merkle root of the code group for `po2` (risc0: the control-ID table entry)."""
+        r = _u32(root)
+        assert r.size == 8
+        _chk(load_library().b2z_circuit_set_control_root(self.h, C.c_uint(po2), _vp(r)))
+
+    def control_root(self, po2: int):
+        r = np.empty(8, dtype=np.uint32)
+        return r if load_library().b2z_circuit_get_control_root(self.h, C.c_uint(po2), _vp(r)) else None
+
+    def verify_receipt(self, receipt: "Receipt", image_id=None):
+        """Receipt::verify(image_id) (/root/reference crates/host/src/bin/cli.rs:103): returns (code, bad_segment)."""
+        bad = C.c_size_t()
+        iid = _vp(_u32(image_id)) if image_id is not None else None
+        rc = int(load_library().b2z_verify_receipt(self.h, receipt.ptr, iid, C.byref(bad)))
+        return rc, int(bad.value)
 
     @staticmethod
     def precompile(blob):
@@ -221,6 +259,17 @@ class Hal:
     def gather_sample(self, dst: int, src: int, idx: int, size: int, stride: int):
         _chk(self.L.b2z_gather_sample(self.ctx, C.c_void_p(dst), C.c_void_p(src), C.c_size_t(idx), C.c_size_t(size), C.c_size_t(stride)))
 
+    def scatter(self, into: int, index: int, offsets: int, values: int, count: int):
+        _chk(self.L.b2z_scatter(self.ctx, C.c_void_p(into), C.c_void_p(index), C.c_void_p(offsets), C.c_void_p(values), C.c_size_t(count)))
+
+    def prefix_products(self, ext_io: int, n: int):
+        _chk(self.L.b2z_prefix_products(self.ctx, C.c_void_p(ext_io), C.c_size_t(n)))
+
+    def compute_control_root(self, po2: int, code_dev: int, code_cols: int) -> np.ndarray:
+        root = np.empty(8, dtype=np.uint32)
+        _chk(self.L.b2z_compute_control_root(self.ctx, C.c_uint(po2), C.c_void_p(code_dev), C.c_size_t(code_cols), _vp(root)))
+        return root
+
     def poly_divide(self, ext_coeffs: int, count: int, z) -> np.ndarray:
         z = _u32(z)
         rem = np.empty(4, dtype=np.uint32)
@@ -269,3 +318,172 @@ class Hal:
         buf = (C.c_double * 32)()
         n = int(self.L.b2z_last_phase_ms(self.ctx, buf, C.c_size_t(32)))
         return {self.L.b2z_phase_name(i).decode(): buf[i] for i in range(min(n, 32))}
+
+
+# ---- session level: Prover::prove -> Receipt (risc0-zkvm; /root/reference crates/host/src/lib.rs:131-142) ----
+class SegmentInput(C.Structure):
+    _fields_ = [("index", C.c_uint32), ("po2", C.c_uint32), ("code", C.c_void_p), ("data", C.c_void_p), ("globals", C.c_void_p),
+                ("accum_noise", C.c_void_p), ("zk_rows", C.c_size_t), ("on_device", C.c_int)]
+
+
+class SegmentReceiptStruct(C.Structure):
+    _fields_ = [("index", C.c_uint32), ("po2", C.c_uint32), ("hashfn", C.c_char * 16), ("verifier_parameters", C.c_uint32 * 8),
+                ("claim_pre", C.c_uint32 * 8), ("claim_post", C.c_uint32 * 8), ("seal", C.POINTER(C.c_uint32)), ("seal_words", C.c_size_t)]
+
+
+class ReceiptStruct(C.Structure):
+    _fields_ = [("segments", C.POINTER(SegmentReceiptStruct)), ("n_segments", C.c_size_t), ("verifier_parameters", C.c_uint32 * 8),
+                ("journal", C.POINTER(C.c_uint8)), ("journal_len", C.c_size_t)]
+
+
+class Receipt:
+    """Owner of a b2z_receipt (Receipt{inner: Composite{segments}, journal}); `segments[i]` exposes the C fields."""
+
+    def __init__(self, ptr):
+        self.ptr = ptr  # POINTER(ReceiptStruct)
+
+    @property
+    def n_segments(self) -> int:
+        return int(self.ptr.contents.n_segments)
+
+    def segment(self, i: int) -> SegmentReceiptStruct:
+        assert 0 <= i < self.n_segments
+        return self.ptr.contents.segments[i]
+
+    def seal(self, i: int) -> np.ndarray:
+        s = self.segment(i)
+        return np.ctypeslib.as_array(s.seal, shape=(int(s.seal_words),)).copy()
+
+    def claim(self, i: int):
+        s = self.segment(i)
+        return np.array(list(s.claim_pre), dtype=np.uint32), np.array(list(s.claim_post), dtype=np.uint32)
+
+    @property
+    def journal(self) -> bytes:
+        r = self.ptr.contents
+        return bytes(bytearray(r.journal[i] for i in range(int(r.journal_len))))
+
+    def serialize(self) -> bytes:
+        L = load_library()
+        buf = C.POINTER(C.c_uint8)()
+        n = C.c_size_t()
+        _chk(L.b2z_receipt_serialize(self.ptr, C.byref(buf), C.byref(n)))
+        out = C.string_at(buf, n.value)
+        L.b2z_bytes_free(buf)
+        return out
+
+    @staticmethod
+    def deserialize(data: bytes) -> "Receipt":
+        p = C.POINTER(ReceiptStruct)()
+        b = (C.c_uint8 * len(data)).from_buffer_copy(data) if data else (C.c_uint8 * 1)()
+        _chk(load_library().b2z_receipt_deserialize(b, C.c_size_t(len(data)), C.byref(p)))
+        return Receipt(p)
+
+    @staticmethod
+    def assemble(circuit: Circuit, seals, journal: bytes = b"") -> "Receipt":
+        seals = [_u32(s) for s in seals]
+        ptrs = (C.c_void_p * max(len(seals), 1))(*[s.ctypes.data for s in seals])
+        lens = (C.c_size_t * max(len(seals), 1))(*[s.size for s in seals])
+        p = C.POINTER(ReceiptStruct)()
+        j = (C.c_uint8 * max(len(journal), 1)).from_buffer_copy(journal.ljust(1, b"\0"))
+        _chk(load_library().b2z_receipt_assemble(circuit.h, ptrs, lens, C.c_size_t(len(seals)), j, C.c_size_t(len(journal)), C.byref(p)))
+        return Receipt(p)
+
+    def close(self):
+        if self.ptr:
+            load_library().b2z_receipt_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _SessionCircuit(Circuit):
+    """View of a session worker's circuit (owned by the session: never freed from here)."""
+
+    def __init__(self, handle):
+        L = load_library()
+        self.h = C.c_void_p(handle)
+        self.blob = None
+        self.group_sizes = tuple(int(L.b2z_circuit_group_size(self.h, C.c_int(g))) for g in range(3))
+        self.globals_size = int(L.b2z_circuit_globals_size(self.h))
+        self.mix_size = int(L.b2z_circuit_mix_size(self.h))
+
+    def close(self):
+        self.h = C.c_void_p()
+
+
+class _SessionHal(Hal):
+    """View of a session worker's context (owned by the session)."""
+
+    def __init__(self, L, ctx, device):
+        self.L = L
+        self.ctx = C.c_void_p(ctx)
+        self.device = device
+
+    def close(self):
+        self.ctx = C.c_void_p()
+
+
+class Session:
+    """A prover server for one circuit on one GPU: `in_flight` segments proved concurrently (own streams), receipts in
+    index order -- ProverServer::prove_session behind `default_prover().prove(env, elf)`."""
+
+    def __init__(self, device: int, blob, in_flight: int = 2):
+        L = load_library()
+        self.L = L
+        self.blob = _u32(blob)
+        self.h = C.c_void_p()
+        _chk(L.b2z_session_create(C.c_int(device), _vp(self.blob), C.c_size_t(self.blob.size), C.c_uint(in_flight), C.byref(self.h)))
+        self.device = device
+        self.in_flight = int(L.b2z_session_in_flight(self.h))
+        self.circuit = _SessionCircuit(L.b2z_session_circuit(self.h))
+        self.hals = [_SessionHal(L, L.b2z_session_context(self.h, C.c_uint(i)), device) for i in range(self.in_flight)]
+
+    def set_control_root(self, po2: int, root):
+        r = _u32(root)
+        _chk(self.L.b2z_session_set_control_root(self.h, C.c_uint(po2), _vp(r)))
+
+    def prove(self, segments, journal: bytes = b"") -> Receipt:
+        """segments: list of dicts {po2, code, data, globals, accum_noise, zk_rows, on_device}; code/data/accum_noise are
+        device pointers (ints) when on_device, else numpy arrays / host pointers."""
+        keep = []
+
+        def hp(x):
+            if isinstance(x, np.ndarray):
+                keep.append(x)
+                return x.ctypes.data
+            return int(x)
+        arr = (SegmentInput * max(len(segments), 1))()
+        for i, s in enumerate(segments):
+            g = _u32(s["globals"])
+            keep.append(g)
+            arr[i] = SegmentInput(s.get("index", i), s["po2"], hp(s["code"]), hp(s["data"]), g.ctypes.data, hp(s["accum_noise"]),
+                                  s["zk_rows"], 1 if s.get("on_device") else 0)
+        p = C.POINTER(ReceiptStruct)()
+        j = (C.c_uint8 * max(len(journal), 1)).from_buffer_copy(journal.ljust(1, b"\0"))
+        _chk(self.L.b2z_prove_session(self.h, arr, C.c_size_t(len(segments)), j, C.c_size_t(len(journal)), C.byref(p)))
+        return Receipt(p)
+
+    def launch_count(self) -> int:
+        return int(self.L.b2z_session_launch_count(self.h))
+
+    def last_wall_ms(self) -> float:
+        return float(self.L.b2z_session_last_wall_ms(self.h))
+
+    def last_retries(self) -> int:
+        return int(self.L.b2z_session_last_retries(self.h))
+
+    def close(self):
+        if self.h:
+            self.L.b2z_session_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
