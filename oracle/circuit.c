@@ -48,7 +48,7 @@ struct or_circuit {
   uint32_t *wit_store_col, *wit_store_var;
   uint32_t *accum_col;   /* data column feeding accumulator k */
   uint32_t *pin_col, *pin_global;
-  uint8_t *col_kind;     /* per data column: 0 free, 1 free bit, 2 derived */
+  uint32_t *col_kind;    /* per data column: 0 free, 1 free bit, 2 derived, 3 | idx << 8 | size << 16 | group << 24 one-hot member */
   size_t n_wit_fp;
   /* control roots (risc0: control IDs): expected Merkle root of the code group per po2 (verify/mod.rs check_code) */
   uint32_t control_root[32][8];
@@ -141,8 +141,8 @@ or_circuit *or_circuit_load(const uint32_t *blob, size_t words) {
     c->pin_col[i] = blob[pos++];
     c->pin_global[i] = blob[pos++];
   }
-  c->col_kind = (uint8_t *)malloc(c->group_size[2] + 1);
-  for (size_t i = 0; i < c->group_size[2]; i++) c->col_kind[i] = (uint8_t)blob[pos++];
+  c->col_kind = (uint32_t *)malloc(4 * (c->group_size[2] + 1));
+  for (size_t i = 0; i < c->group_size[2]; i++) c->col_kind[i] = blob[pos++];
 
   /* registers: runs of taps sharing (group, offset) -- taps.rs TapSet::regs() */
   c->reg_group = (uint32_t *)malloc(4 * (c->n_taps + 1));
@@ -381,6 +381,10 @@ void or_witgen(const or_circuit *c, unsigned po2, fp *code, fp *data, fp *global
       if (r >= active_rows) v = or_synth_rand(seed, STREAM_NOISE, (uint32_t)col, r);
       else if (c->col_kind[col] == 0) v = or_synth_rand(seed, STREAM_FREE, (uint32_t)col, r);
       else if (c->col_kind[col] == 1) v = (or_synth_rand(seed, STREAM_FREE, (uint32_t)col, r) & 1) ? FP_ONE : 0;
+      else if ((c->col_kind[col] & 0xff) == 3) { /* one-hot group: member idx is 1 on the rows whose group draw selects it */
+        uint32_t k = c->col_kind[col], idx = (k >> 8) & 0xff, size = (k >> 16) & 0xff, grp = k >> 24;
+        v = (or_synth_rand(seed, STREAM_FREE, 0x8000u + grp, r) % size) == idx ? FP_ONE : 0;
+      }
       data[col * n + r] = v;
     }
   for (size_t g = 0; g < c->globals_size; g++) globals[g] = or_synth_rand(seed, STREAM_FREE, 0xffff, g);

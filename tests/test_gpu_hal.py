@@ -422,3 +422,30 @@ def test_negative_c_abi_arguments(hal):
     with pytest.raises(H.B2ZError, match="in_flight"):
         H.Session(0, np.zeros(64, dtype=np.uint32), in_flight=0)
     hal.free(d)
+
+
+# ---- two-pass transforms (ntt_big.cuh): every size 2^20 .. 2^24, several columns, both directions ----
+@pytest.mark.parametrize("in_po2,count", [(18, 5), (19, 3), (20, 3), (21, 2), (22, 2)])
+def test_two_pass_expand_ntt(hal, oracle, in_po2, count):
+    rng = np.random.default_rng(500 + in_po2)
+    x = rand_fp(rng, count << in_po2)
+    d = hal.copy_from(x)
+    o = hal.alloc(count << (in_po2 + 2))
+    hal.batch_expand_into_evaluate_ntt(o, d, count, in_po2, 2)
+    got = hal.view(o, count << (in_po2 + 2))
+    hal.free(d)
+    hal.free(o)
+    assert np.array_equal(got, oracle.batch_expand_into_evaluate_ntt(x, count, 2))
+
+
+@pytest.mark.parametrize("po2,count", [(20, 5), (21, 3), (22, 3), (23, 2), (24, 1)])
+def test_two_pass_interpolate_and_evaluate(hal, oracle, po2, count):
+    rng = np.random.default_rng(600 + po2)
+    x = rand_fp(rng, count << po2)
+    d = hal.copy_from(x)
+    hal.batch_interpolate_ntt(d, count, po2)
+    got = hal.view(d, x.size)
+    assert np.array_equal(got, oracle.batch_interpolate_ntt(x, count))
+    hal.batch_evaluate_ntt(d, count, po2, 0)  # forward, in place, no expand: back to the evaluations
+    assert np.array_equal(hal.view(d, x.size), x)
+    hal.free(d)

@@ -68,7 +68,11 @@ b2z_err circuit_parse(b2z_circuit* c, const uint32_t* blob, size_t words) {
     c->pin_col.push_back(blob[pos++]);
     c->pin_global.push_back(blob[pos++]);
   }
-  for (size_t i = 0; i < c->group_size[2]; i++) c->col_kind.push_back((uint8_t)blob[pos++]);
+  for (size_t i = 0; i < c->group_size[2]; i++) {
+    uint32_t k = blob[pos++];
+    B2Z_REQUIRE(k <= 2 || ((k & 0xff) == 3 && ((k >> 16) & 0xff) > ((k >> 8) & 0xff)), "circuit blob: bad data column kind");
+    c->col_kind.push_back(k);
+  }
   B2Z_REQUIRE(c->mix_size >= 4 * n_accum, "circuit blob: mix too small for the accumulators");
   B2Z_REQUIRE(c->group_size[0] >= 4 * n_accum, "circuit blob: accum group too small");
 
@@ -521,8 +525,21 @@ void circuit_codegen(b2z_circuit* c) {
     }
     result = mixv[c->ret];
   }
-  const std::string kernel_head_params = "u32* __restrict__ check, const __grid_constant__ ColPtrs cp, const __grid_constant__ Consts kc, "
-                                         "u32 iz0, u32 iz1, u32 iz2, u32 iz3, u64 mask";
+  // parts mode reads its tables from module __constant__ memory (ccp / ckc): the two structs must NOT also travel as kernel
+  // parameters (a program of the rv32im size class has ~45 KB of poly_mix powers; the parameter space is 32 KB)
+  const std::string kernel_head_params =
+      parts_m > 0 ? std::string("u32* __restrict__ check, u32 iz0, u32 iz1, u32 iz2, u32 iz3, u64 mask")
+                  : std::string("u32* __restrict__ check, const __grid_constant__ ColPtrs cp, const __grid_constant__ Consts kc, "
+                                "u32 iz0, u32 iz1, u32 iz2, u32 iz3, u64 mask");
+  // B2Z_EVALCHECK_THREADS = T (parts mode, one point per thread): CTA size.  With T > 128 the CTA's warps are held together by a
+  // barrier after every part, so a part's instructions are fetched from L2 once per CTA and stay in the SM's instruction
+  // cache while all of its warps run them -- a straight-line program of megabytes otherwise streams once per WARP.
+  int cta_threads = 128;
+  if (const char* e = getenv("B2Z_EVALCHECK_THREADS")) cta_threads = atoi(e);
+  if (cta_threads != 256 && cta_threads != 512 && cta_threads != 1024) cta_threads = 128;
+  if (parts_m <= 0 || points_k != 1) cta_threads = 128;
+  c->eval_threads = (unsigned)cta_threads;
+  const bool cta_sync = cta_threads > 128;
   auto emit_tail = [&](std::ostringstream& out) {
     out << "  const u32 iz = (i & 2) ? ((i & 1) ? iz3 : iz2) : ((i & 1) ? iz1 : iz0);\n";
     for (int k = 0; k < 4; k++) {
@@ -586,10 +603,30 @@ void circuit_codegen(b2z_circuit* c) {
       for (size_t j = 0; j < outs.size(); j++) main_body << "  const u32 t" << outs[j] << " = r" << p << ".v[" << j << "];\n";
     }
     if (points_k == 1) {
-      o << "extern \"C\" __global__ void __launch_bounds__(128, " << min_blocks << ") b2z_eval_check(" << kernel_head_params << ") {\n";
-      o << "  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;\n  if (i > mask) return;\n  const u64 domain = mask + 1;\n";
+      // same register cap as the 128-thread kernel (56): min_blocks CTAs of 128 threads == min_blocks * 128 / T CTAs of T threads
+      const int mb = std::max(1, min_blocks * 128 / cta_threads);
+      o << "extern \"C\" __global__ void __launch_bounds__(" << cta_threads << ", " << mb << ") b2z_eval_check(" << kernel_head_params << ") {\n";
+      if (!cta_sync) {
+        o << "  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;\n  if (i > mask) return;\n  const u64 domain = mask + 1;\n";
+      } else {
+        // every thread must reach the barriers: out-of-range threads (domains smaller than a CTA) evaluate point `mask` and skip the store
+        o << "  const u64 i0 = (u64)blockIdx.x * blockDim.x + threadIdx.x;\n  const u64 i = i0 > mask ? mask : i0;\n  const u64 domain = mask + 1;\n";
+      }
       for (unsigned b = 0; b <= max_back; b++) o << "  const u32 ib" << b << " = (u32)((i - " << 4 * b << "ull) & mask) << 2;\n";
-      o << main_body.str();
+      if (cta_sync) {
+        std::string body = main_body.str(), synced;
+        size_t pos = 0, nl;
+        while ((nl = body.find('\n', pos)) != std::string::npos) {  // a barrier before every part call
+          std::string line = body.substr(pos, nl - pos + 1);
+          if (line.find(" = part") != std::string::npos) synced += "  __syncthreads();\n";
+          synced += line;
+          pos = nl + 1;
+        }
+        o << synced;
+        o << "  if (i0 > mask) return;\n";
+      } else {
+        o << main_body.str();
+      }
       emit_tail(o);
     } else {
       // K points per thread: point k of a thread is (blockIdx.x * K + k) * 128 + threadIdx.x (every k-slice is coalesced);
@@ -713,6 +750,7 @@ b2z_err circuit_cubin(b2z_circuit* c, std::vector<char>& cubin, bool force_recom
   std::string tmp = path + ".tmp.XXXXXX";
   int fd = mkstemp(&tmp[0]);
   if (fd >= 0) {
+    fchmod(fd, 0644);
     bool ok = write(fd, cubin.data(), cubin.size()) == (ssize_t)cubin.size() && fsync(fd) == 0;
     close(fd);
     if (ok) ok = rename(tmp.c_str(), path.c_str()) == 0;
@@ -744,8 +782,8 @@ b2z_err circuit_compile(b2z_ctx* ctx, b2z_circuit* c) {
     B2Z_CUDA(cudaMemcpy(c->accum_col_dev, c->accum_col.data(), 4 * c->accum_col.size(), cudaMemcpyHostToDevice));
   }
   if (!c->col_kind.empty()) {
-    B2Z_CUDA(cudaMalloc(&c->col_kind_dev, c->col_kind.size()));
-    B2Z_CUDA(cudaMemcpy(c->col_kind_dev, c->col_kind.data(), c->col_kind.size(), cudaMemcpyHostToDevice));
+    B2Z_CUDA(cudaMalloc(&c->col_kind_dev, 4 * c->col_kind.size()));
+    B2Z_CUDA(cudaMemcpy(c->col_kind_dev, c->col_kind.data(), 4 * c->col_kind.size(), cudaMemcpyHostToDevice));
   }
   return nullptr;
 }

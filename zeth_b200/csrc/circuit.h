@@ -19,7 +19,7 @@ struct b2z_circuit {
   size_t n_combos = 0, tot_combo_backs = 0;
   std::vector<Step> steps, wit_steps;
   std::vector<uint32_t> wit_store_col, wit_store_var, accum_col, pin_col, pin_global;
-  std::vector<uint8_t> col_kind;
+  std::vector<uint32_t> col_kind;  // 0 free, 1 free bit, 2 derived, 3 | idx << 8 | size << 16 | group << 24 one-hot member
   // static analysis
   std::vector<uint8_t> fp_is_ext;
   std::vector<uint32_t> mix_exp;
@@ -30,6 +30,7 @@ struct b2z_circuit {
   cudaLibrary_t library = nullptr;
   cudaKernel_t k_eval_check = nullptr, k_witgen = nullptr;
   bool parts_mode = false;                    // eval_check split into __noinline__ parts; tables in module constants
+  unsigned eval_threads = 128;                // CTA size of the generated eval_check (B2Z_EVALCHECK_THREADS)
   unsigned points_per_thread = 1;             // coset points per thread of the generated eval_check (parts mode, B2Z_EVALCHECK_POINTS)
   void *ccp_dev = nullptr, *ckc_dev = nullptr;  // device addresses of the module's __constant__ tables (parts mode)
   // control roots (risc0: control IDs): expected Merkle root of the code group per po2, checked by the verifier
@@ -38,7 +39,7 @@ struct b2z_circuit {
   // device-resident tables
   int device = -1;
   uint32_t* accum_col_dev = nullptr;
-  uint8_t* col_kind_dev = nullptr;
+  uint32_t* col_kind_dev = nullptr;
 };
 
 namespace b2z {

@@ -629,6 +629,10 @@ static b2z_err launch_one(b2z_ctx* ctx, const PassArgs& a, unsigned R) {
 #undef B2Z_NTT_CASE
 }
 
+}  // namespace b2z
+#include "ntt_big.cuh"
+namespace b2z {
+
 // forward transform of `count` columns: out (2^logn per column) from in (2^(logn - ebits) per column when expanding)
 b2z_err launch_evaluate(b2z_ctx* ctx, uint32_t* out, const uint32_t* in, size_t count, unsigned out_po2, unsigned expand_bits) {
   if (count == 0) return nullptr;
@@ -639,6 +643,9 @@ b2z_err launch_evaluate(b2z_ctx* ctx, uint32_t* out, const uint32_t* in, size_t 
     if (expanding) B2Z_CUDA(cudaMemcpyAsync(out, in, 4 * count, cudaMemcpyDeviceToDevice, ctx->stream));
     return nullptr;
   }
+  // 2^20 .. 2^24 points: two round trips through HBM instead of three (ntt_big.cuh)
+  if (big_applies(logn) && ((expanding && expand_bits == 2 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) || (!expanding && expand_bits == 0)))
+    return launch_big_evaluate(ctx, out, in, count, logn, expanding);
   unsigned R[8], np = 0;
   plan_passes(logn, R, &np);
   B2Z_REQUIRE(expand_bits <= 2 && expand_bits <= (R[0] < 4 ? R[0] : 4), "expand_bits larger than the first radix group");
@@ -692,6 +699,7 @@ b2z_err launch_interpolate(b2z_ctx* ctx, uint32_t* io, size_t count, unsigned po
     return nullptr;
   }
   uint32_t norm = fp_inv(fp_from_u32((uint32_t)(((uint64_t)1 << po2) % P)));
+  if (big_applies(logn)) return launch_big_interpolate(ctx, io, src, count, logn, norm, fuse_zk_shift ? ctx->pow3rev[po2] : nullptr);
   unsigned R[8], np = 0;
   plan_passes(logn, R, &np);
   const uint32_t* pass_tw[8] = {};

@@ -254,7 +254,7 @@ b2z_err prove_segment_device(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, c
   const size_t wa = c->group_size[0], wc = c->group_size[1], wd = c->group_size[2];
   const size_t gsz = c->globals_size, msz = c->mix_size;
   const size_t seal_words = circuit_seal_words(c, po2);
-  B2Z_TRY(ensure_pinned(ctx, seal_words + 64 + 4 * (c->n_taps + 64) + 4 * (c->tot_combo_backs + 8)));
+  B2Z_TRY(ensure_pinned(ctx, seal_words + 64 + 4 * (c->n_taps + 64) + 4 * (c->tot_combo_backs + 8) + 16));
   Seal seal{ctx->pinned, 0, seal_words};
   uint32_t* scratch = ctx->pinned + seal_words + 8;  // [root(8)] [eval_u ...] [DEEP remainders]
   uint32_t* rem_host = ctx->pinned + seal_words + 64 + 4 * (c->n_taps + 64);
@@ -323,8 +323,21 @@ b2z_err prove_segment_device(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, c
   tm.end(4);
   tm.begin(5);
   B2Z_TRY(launch_interpolate(ctx, check, 4, po2 + 2, false));
+  // Satisfiability check (upstream only debug-asserts; an unsatisfied witness would otherwise yield a well-formed but
+  // invalid seal): constraints have degree <= 5 in taps of degree < N, so C(x) / (x^N - 1) has degree <= 4N - 5 and the four
+  // highest coefficients of every component of the check polynomial are zero.  If some constraint fails on the trace, C is
+  // not divisible by x^N - 1 and the interpolant of its coset values has full degree (with overwhelming probability).
+  // The 16 words ride along with the next transcript round trip.
+  uint32_t* top_host = rem_host + 4 * (c->tot_combo_backs + 2);
+  for (unsigned t = 0; t < 4; t++) {
+    const size_t slot = bit_rev((uint32_t)(domain - 1 - t), po2 + 2);  // coefficients are in bit-reversed order
+    B2Z_CUDA(cudaMemcpy2DAsync(top_host + 4 * t, 4, check + slot, 4 * domain, 4, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  }
   // bit-reversed 4N coefficients per component = 4 quarters of N: the 16 x N check group, no data movement
   B2Z_TRY(poly_group_commit(ctx, mem, check_pg, check, B2Z_CHECK_SIZE, po2, seal, rng));
+  for (unsigned i = 0; i < 16; i++)
+    if (top_host[i] != 0)
+      return set_error("witness does not satisfy the circuit: the check polynomial has degree > 4N - 5 (some constraint fails on the trace)");
   tm.end(5);
 
   tm.begin(6);
