@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_json_line():
-    env = dict(os.environ, B2Z_REF_MIN_PO2="12", B2Z_REF_TARGET_S="1")  # tiny sample: this test checks the contract, not the number
+    env = dict(os.environ, B2Z_REF_PO2="9")  # tiny sample: this test checks the contract, not the number
     env.pop("RANK", None)
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
                          capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
@@ -16,10 +16,11 @@ def test_reference_arm_json_line():
     lines = [ln for ln in out.stdout.strip().splitlines() if ln.strip()]
     assert len(lines) == 1
     d = json.loads(lines[0])
-    assert d["impl"] == "reference" and d["metric"] == "rv32im_cycles_proved_per_sec" and d["unit"] == "cycles/s"
+    assert d["impl"] == "reference" and d["metric"] == "zkvm_cycles_proved_per_sec" and d["unit"] == "cycles/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["vs_baseline"] is None
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "cycles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["circuit_steps"] >= 27000 and d["config"]["host"]["omp_threads"] == d["cpu_baseline"]["cores"]
 
 
 def test_reference_arm_other_ranks_exit_quietly():

@@ -331,3 +331,34 @@ def test_prove_session_receipts(hal, oracle):
     r3 = sess.prove(wit[:2])
     assert np.array_equal(r3.seal(1), want[1])
     sess.close()
+
+
+# ---- circuits of the rv32im shape: one-hot mode selectors, AndCond-gated blocks, back taps up to 7 ----
+@pytest.mark.parametrize("mk,po2", [(S.circuit_mux_small, 7), (S.circuit_mux_small, 11), (S.circuit_rv32im_scale, 10)])
+def test_mux_circuit_seal_parity(hal, oracle, mk, po2):
+    """GPU witgen == oracle witgen (one-hot column kinds), eval_check == oracle interpreter on the LDEs, whole seal ==
+    oracle seal; for the rv32im-scale program (27 542 steps, 1 038 taps, 547 generated device functions) at po2 = 10."""
+    sc = mk()
+    oc, code, data, glob, noise, zk = _witness(oracle, sc, po2, 5 + po2)
+    n = 1 << po2
+    wa, wc, wd = sc.group_sizes
+    c = H.Circuit(hal, sc.blob)
+    dcode, ddata = hal.alloc(wc * n), hal.alloc(wd * n)
+    dglob, dnoise = hal.alloc(sc.globals_size), hal.alloc(wa * zk)
+    hal.witgen(c, po2, dcode, ddata, dglob, dnoise, 5 + po2, zk)
+    assert np.array_equal(hal.view(dcode, wc * n), code)
+    assert np.array_equal(hal.view(ddata, wd * n), data)
+    assert np.array_equal(hal.view(dglob, sc.globals_size), glob)
+    want = oc.prove(po2, code, data, glob, noise, zk)
+    assert oc.verify(want) == 0
+    got = hal.prove_segment_device(c, po2, dcode, ddata, glob, dnoise, zk)
+    diff = np.nonzero(got != want)[0]
+    assert diff.size == 0, f"first differing seal words {diff[:5]} of {want.size}"
+    c.set_control_root(po2, oc.control_roots[po2])
+    assert c.verify(got) == 0
+    bad = data.copy()
+    derived = [col for col in range(sc.w_data) if sc.blob[-sc.w_data:][col] == 2]
+    bad[derived[1] * n + 3] ^= 1
+    with pytest.raises(H.B2ZError, match="does not satisfy"):
+        hal.prove_segment(c, po2, code, bad, glob, noise, zk)
+    c.close()

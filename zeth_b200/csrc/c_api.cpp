@@ -70,6 +70,9 @@ b2z_err b2z_destroy(b2z_ctx* ctx) {
   }
   for (auto e : ctx->h2d_events) cudaEventDestroy(e);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+  if (ctx->aux_fork) cudaEventDestroy(ctx->aux_fork);
+  if (ctx->aux_join) cudaEventDestroy(ctx->aux_join);
   cudaStreamDestroy(ctx->own_stream);
   delete ctx;
   return nullptr;

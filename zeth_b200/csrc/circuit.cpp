@@ -320,7 +320,7 @@ struct Emitter {
     std::vector<unsigned> uses;
   };
   std::vector<Stmt>* stmts = nullptr;
-  std::string cp_name = "cp", kc_name = "kc";
+  std::string cp_name = "cp", kc_name = "kc", glob_name = "globals";
   Opd emit(const std::string& expr, const Opd* a = nullptr, const Opd* b = nullptr) {
     unsigned id = tmp++;
     std::string n = "t" + std::to_string(id);
@@ -429,7 +429,7 @@ struct Emitter {
         if (trace_domain) {
           r.ext = false;
           r.leaf_load = true;
-          r.load_expr = "ldv(globals + " + std::to_string(s.b) + ")";
+          r.load_expr = "ldv(" + glob_name + " + " + std::to_string(s.b) + ")";
         } else {
           r = base(named(kc_name + (s.a == 0 ? ".g[" : ".m[") + std::to_string(s.b) + "]"));
         }
@@ -674,19 +674,90 @@ void circuit_codegen(b2z_circuit* c) {
     }
   }
   // ---- witgen: one thread per active trace row; taps read the trace domain (stride 1) ----
-  o << "extern \"C\" __global__ void __launch_bounds__(256) b2z_witgen(const __grid_constant__ ColPtrs cp, "
-       "const u32* __restrict__ globals, u64 mask, u64 active_rows) {\n";
-  o << "  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;\n  if (i >= active_rows) return;\n";
-  for (unsigned b = 0; b <= max_back; b++) o << "  const u32 ib" << b << " = (u32)((i - " << b << "ull) & mask) << 2;\n";
-  {
+  if (parts_m <= 0) {
+    o << "extern \"C\" __global__ void __launch_bounds__(256) b2z_witgen(const __grid_constant__ ColPtrs cp, "
+         "const u32* __restrict__ globals, u64 mask, u64 active_rows) {\n";
+    o << "  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;\n  if (i >= active_rows) return;\n";
+    for (unsigned b = 0; b <= max_back; b++) o << "  const u32 ib" << b << " = (u32)((i - " << b << "ull) & mask) << 2;\n";
     Emitter em{c, true, &o, {}, 0};
     for (const auto& s : c->wit_steps) em.step(s);
     for (size_t k = 0; k < c->wit_store_col.size(); k++) {
       Val v = em.use(c->wit_store_var[k]);
       o << "  const_cast<u32*>(cp.g2[" << c->wit_store_col[k] << "])[i] = " << v.c[0].str() << ";\n";
     }
+    o << "}\n";
+  } else {
+    // Partitioned like eval_check: one huge basic block (a mux circuit's witgen program has tens of thousands of
+    // statements) makes ptxas scheduling super-linear -- minutes to hours of compile time.  Cuts are allowed right after a
+    // stored value has been computed; column pointers and the globals pointer live in module __constant__ memory.
+    o << "__constant__ ColPtrs wcp;\n__constant__ const u32* wglobals;\n";
+    std::vector<Emitter::Stmt> wst;
+    Emitter em{c, true, &o, {}, 0};
+    em.stmts = &wst;
+    em.cp_name = "wcp";
+    em.glob_name = "wglobals";
+    for (const auto& s : c->wit_steps) em.step(s);
+    struct Store {
+      uint32_t col;
+      Opd v;
+    };
+    std::vector<Store> stores;
+    for (size_t k = 0; k < c->wit_store_col.size(); k++) stores.push_back({c->wit_store_col[k], em.use(c->wit_store_var[k]).c[0]});
+    std::map<unsigned, size_t> pos_of;  // temporary id -> statement index
+    for (size_t k = 0; k < wst.size(); k++) pos_of[wst[k].id] = k;
+    std::vector<size_t> cuts;
+    for (const auto& st : stores)
+      if (st.v.tid >= 0) cuts.push_back(pos_of[(unsigned)st.v.tid] + 1);
+    std::sort(cuts.begin(), cuts.end());
+    std::vector<size_t> bounds{0};
+    for (size_t cp_i : cuts)
+      if (cp_i >= bounds.back() + (size_t)parts_m) bounds.push_back(cp_i);
+    if (bounds.back() != wst.size()) bounds.push_back(wst.size());
+    std::map<unsigned, size_t> def_part, last_use_part;
+    for (size_t p = 0; p + 1 < bounds.size(); p++)
+      for (size_t k = bounds[p]; k < bounds[p + 1]; k++) {
+        def_part[wst[k].id] = p;
+        for (unsigned u : wst[k].uses) last_use_part[u] = p;
+      }
+    const size_t FINAL = bounds.size();
+    for (const auto& st : stores)
+      if (st.v.tid >= 0) last_use_part[(unsigned)st.v.tid] = FINAL;  // stored by the kernel body right after its part returns
+    std::ostringstream wmain;
+    for (size_t p = 0; p + 1 < bounds.size(); p++) {
+      std::vector<unsigned> ins, outs;
+      std::map<unsigned, bool> seen;
+      for (size_t k = bounds[p]; k < bounds[p + 1]; k++) {
+        for (unsigned u : wst[k].uses)
+          if (def_part[u] < p && !seen[u]) {
+            seen[u] = true;
+            ins.push_back(u);
+          }
+        if (last_use_part.count(wst[k].id) && last_use_part[wst[k].id] > p) outs.push_back(wst[k].id);
+      }
+      o << "struct WR" << p << " { u32 v[" << (outs.empty() ? 1 : outs.size()) << "]; };\n";
+      o << "static __device__ __noinline__ WR" << p << " wpart" << p << "(" << ib_params;
+      for (unsigned u : ins) o << ", u32 t" << u;
+      o << ") {\n";
+      for (size_t k = bounds[p]; k < bounds[p + 1]; k++) o << "  const u32 t" << wst[k].id << " = " << wst[k].expr << ";\n";
+      o << "  WR" << p << " r;\n";
+      if (outs.empty()) o << "  r.v[0] = 0u;\n";
+      for (size_t jj = 0; jj < outs.size(); jj++) o << "  r.v[" << jj << "] = t" << outs[jj] << ";\n";
+      o << "  return r;\n}\n";
+      wmain << "  const WR" << p << " w" << p << " = wpart" << p << "(" << ib_args;
+      for (unsigned u : ins) wmain << ", t" << u;
+      wmain << ");\n";
+      for (size_t jj = 0; jj < outs.size(); jj++) wmain << "  const u32 t" << outs[jj] << " = w" << p << ".v[" << jj << "];\n";
+      for (const auto& st : stores)
+        if (st.v.tid >= 0 && def_part[(unsigned)st.v.tid] == p)
+          wmain << "  const_cast<u32*>(wcp.g2[" << st.col << "])[i] = t" << st.v.tid << ";\n";
+    }
+    for (const auto& st : stores)
+      if (st.v.tid < 0) wmain << "  const_cast<u32*>(wcp.g2[" << st.col << "])[i] = " << st.v.str() << ";\n";
+    o << "extern \"C\" __global__ void __launch_bounds__(256) b2z_witgen(u64 mask, u64 active_rows) {\n";
+    o << "  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;\n  if (i >= active_rows) return;\n";
+    for (unsigned b = 0; b <= max_back; b++) o << "  const u32 ib" << b << " = (u32)((i - " << b << "ull) & mask) << 2;\n";
+    o << wmain.str() << "}\n";
   }
-  o << "}\n";
   c->source = o.str();
   uint64_t h = 1469598103934665603ull;
   for (unsigned char ch : c->source) {
@@ -775,6 +846,8 @@ b2z_err circuit_compile(b2z_ctx* ctx, b2z_circuit* c) {
     size_t bytes = 0;
     B2Z_CUDA(cudaLibraryGetGlobal(&c->ccp_dev, &bytes, c->library, "ccp"));
     B2Z_CUDA(cudaLibraryGetGlobal(&c->ckc_dev, &bytes, c->library, "ckc"));
+    B2Z_CUDA(cudaLibraryGetGlobal(&c->wcp_dev, &bytes, c->library, "wcp"));
+    B2Z_CUDA(cudaLibraryGetGlobal(&c->wglobals_dev, &bytes, c->library, "wglobals"));
   }
   c->device = ctx->device;
   if (!c->accum_col.empty()) {

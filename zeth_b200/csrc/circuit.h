@@ -33,6 +33,7 @@ struct b2z_circuit {
   unsigned eval_threads = 128;                // CTA size of the generated eval_check (B2Z_EVALCHECK_THREADS)
   unsigned points_per_thread = 1;             // coset points per thread of the generated eval_check (parts mode, B2Z_EVALCHECK_POINTS)
   void *ccp_dev = nullptr, *ckc_dev = nullptr;  // device addresses of the module's __constant__ tables (parts mode)
+  void *wcp_dev = nullptr, *wglobals_dev = nullptr;  // witgen: trace column pointers and the globals pointer (parts mode)
   // control roots (risc0: control IDs): expected Merkle root of the code group per po2, checked by the verifier
   uint32_t control_root[32][8] = {};
   bool has_control_root[32] = {};

@@ -50,6 +50,8 @@ struct b2z_ctx {
   uint64_t launches = 0;
   // per-size device table, built lazily: 3^rev(j) for zk_shift (NTT twist tables live in kernels_ntt.cu's registry)
   uint32_t* pow3rev[b2z::MAX_PO2 + 1] = {};
+  cudaStream_t aux_stream = nullptr;           // second launch stream of the role-split hash kernels (fork / join by events)
+  cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
   unsigned* hash_sched = nullptr;  // tile queue + per-SM role counters of the mixed INT/FP64 hash kernels
   // pinned staging for small transcript round trips
   uint32_t* pinned = nullptr;

@@ -186,6 +186,38 @@ __global__ void __launch_bounds__(128, MINB) hash_rows_mixed_kernel(uint32_t* __
   }
 }
 
+// Role-specialised persistent kernels (B2Z_HASH_SPLIT=1): the same tile queue, but the INT stream and the FP64 stream are
+// two LAUNCHES on two streams.  A mixed kernel is compiled for the larger of the two bodies (80 registers -> 6 CTAs = 24 warps per
+// SM); apart, the INT body needs 48 registers and the FP64 body 80, so an SM can host e.g. 4 + 4 CTAs (32 warps) -- more
+// warps to cover the dependent product chains that keep the mixed kernel's issue rate at ~69 %.
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) hash_rows_int_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ matrix, size_t rows,
+                                                                  size_t cols, uint32_t ones, unsigned* __restrict__ sched, unsigned n_tiles,
+                                                                  unsigned flags) {
+  const unsigned lane = threadIdx.x & 31;
+  for (;;) {
+    unsigned tile = 0;
+    if (lane == 0) tile = atomicAdd(&sched[0], 1u);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    if (tile >= n_tiles) break;
+    size_t r = (size_t)tile * 32 + lane;
+    if (r < rows) hash_row_int(out, matrix, rows, cols, r, ones, flags);
+  }
+}
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) hash_rows_f64_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ matrix, size_t rows,
+                                                                  size_t cols, unsigned* __restrict__ sched, unsigned n_tiles, unsigned flags) {
+  const unsigned lane = threadIdx.x & 31;
+  for (;;) {
+    unsigned tile = 0;
+    if (lane == 0) tile = atomicAdd(&sched[0], 1u);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    if (tile >= n_tiles) break;
+    size_t r = (size_t)tile * 32 + lane;
+    if (r < rows) hash_row_f64(out, matrix, rows, cols, r, flags);
+  }
+}
+
 __global__ void __launch_bounds__(128) hash_fold_kernel(uint32_t* __restrict__ nodes, size_t in_size, size_t out_size, uint32_t ones) {
   size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (j >= out_size) return;
@@ -298,7 +330,28 @@ b2z_err launch_hash_rows_chunk(b2z_ctx* ctx, uint32_t* out, const uint32_t* matr
   const int n_int = env_int("B2Z_HASH_ROLE_INT", 1);            // ... this many run the INT stream, the rest FP64
   const size_t grid = (size_t)ctx->sm_count * ctas_per_sm;
   const size_t min_rows = (size_t)env_int("B2Z_HASH_MIXED_MIN_ROWS", (int)(grid * 128 * 4));
-  if (mixed && period >= 1 && rows >= min_rows && rows / 32 < 0xffffffffu) {
+  const int split = env_int("B2Z_HASH_SPLIT", 0);
+  if (mixed && split && rows >= min_rows && rows / 32 < 0xffffffffu) {
+    // two role-specialised launches sharing one tile queue; the FP64 launch runs on the auxiliary stream (fork / join by events)
+    const int ci = env_int("B2Z_HASH_SPLIT_INT", 4), cf = env_int("B2Z_HASH_SPLIT_F64", 4);
+    if (!ctx->hash_sched) B2Z_CUDA(cudaMalloc(&ctx->hash_sched, HASH_SCHED_WORDS * sizeof(unsigned)));
+    if (!ctx->aux_stream) {
+      B2Z_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+      B2Z_CUDA(cudaEventCreateWithFlags(&ctx->aux_fork, cudaEventDisableTiming));
+      B2Z_CUDA(cudaEventCreateWithFlags(&ctx->aux_join, cudaEventDisableTiming));
+    }
+    B2Z_CUDA(cudaMemsetAsync(ctx->hash_sched, 0, HASH_SCHED_WORDS * sizeof(unsigned), ctx->stream));
+    unsigned n_tiles = (unsigned)((rows + 31) / 32);
+    B2Z_CUDA(cudaEventRecord(ctx->aux_fork, ctx->stream));
+    B2Z_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_fork, 0));
+    if (ci > 0)
+      hash_rows_int_kernel<10><<<(unsigned)(ctx->sm_count * ci), 128, 0, ctx->stream>>>(out, matrix, rows, cols, 0xffffffffu, ctx->hash_sched, n_tiles, flags);
+    if (cf > 0)
+      hash_rows_f64_kernel<6><<<(unsigned)(ctx->sm_count * cf), 128, 0, ctx->aux_stream>>>(out, matrix, rows, cols, ctx->hash_sched, n_tiles, flags);
+    B2Z_CUDA(cudaEventRecord(ctx->aux_join, ctx->aux_stream));
+    B2Z_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->aux_join, 0));
+    ctx->launches++;
+  } else if (mixed && period >= 1 && rows >= min_rows && rows / 32 < 0xffffffffu) {
     if (!ctx->hash_sched) B2Z_CUDA(cudaMalloc(&ctx->hash_sched, HASH_SCHED_WORDS * sizeof(unsigned)));
     B2Z_CUDA(cudaMemsetAsync(ctx->hash_sched, 0, HASH_SCHED_WORDS * sizeof(unsigned), ctx->stream));
     unsigned n_tiles = (unsigned)((rows + 31) / 32);

@@ -28,6 +28,8 @@ namespace b2z {
 // sixteenth roots of unity (Montgomery form): c_w16[j] = w16^j, c_w16i[j] = w16^-j, j < 8
 __constant__ uint32_t c_w16[8];
 __constant__ uint32_t c_w16i[8];
+__constant__ uint32_t c_w16p[8], c_w16s[8];    // plain (non-Montgomery) w16^j and its Shoup companion floor(w16^j * 2^32 / P)
+__constant__ uint32_t c_w16ip[8], c_w16is[8];  // the same for w16^-j
 static bool g_w16_uploaded[16] = {};
 
 __global__ void build_pow3rev_kernel(uint32_t* tab, unsigned bits) {
@@ -92,6 +94,17 @@ b2z_err ensure_tables(b2z_ctx* ctx, unsigned po2, bool pow3) {
     }
     B2Z_CUDA(cudaMemcpyToSymbol(c_w16, w, sizeof w));
     B2Z_CUDA(cudaMemcpyToSymbol(c_w16i, wi, sizeof wi));
+    uint32_t wp[8], ws[8], wip[8], wis[8];
+    for (int j = 0; j < 8; j++) {
+      wp[j] = fp_to_u32(w[j]);
+      wip[j] = fp_to_u32(wi[j]);
+      ws[j] = (uint32_t)((((unsigned __int128)wp[j]) << 32) / P);
+      wis[j] = (uint32_t)((((unsigned __int128)wip[j]) << 32) / P);
+    }
+    B2Z_CUDA(cudaMemcpyToSymbol(c_w16p, wp, sizeof wp));
+    B2Z_CUDA(cudaMemcpyToSymbol(c_w16s, ws, sizeof ws));
+    B2Z_CUDA(cudaMemcpyToSymbol(c_w16ip, wip, sizeof wip));
+    B2Z_CUDA(cudaMemcpyToSymbol(c_w16is, wis, sizeof wis));
     g_w16_uploaded[ctx->device] = true;
   }
   if (pow3 && !ctx->pow3rev[po2]) {
@@ -144,8 +157,19 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void*
 }
 
 // ---- register-level radix-2^Q butterflies with constant sixteenth-root twiddles ----
+// Instruction diet (these kernels are issue-bound: ~200 instructions per element of a 2^24-point transform):
+//   * constant twiddles are Shoup products (IMAD.HI + 2 IMAD + 1 correction = 4 instructions instead of the 5 of a
+//     Montgomery product); a Shoup product accepts ANY 32-bit input, so
+//   * a sum / difference whose only consumer is such a product (or the twist product that follows the group when LAZY_OUT)
+//     is left unreduced in [0, 2P): a + b, resp. a - b + P -- one instruction instead of two.
+// Every value that leaves a kernel is canonical; intermediate tiles may hold [0, 2P) words.
+__device__ __forceinline__ uint32_t mul_shoup(uint32_t x, uint32_t w, uint32_t ws) {  // x < 2^32, w plain < P -> canonical x*w mod P
+  uint32_t q = __umulhi(x, ws);
+  uint32_t r = x * w - q * P;  // in [0, 2P)
+  return umin32(r, r - P);
+}
 // forward: decimation in time, layers FIRST..Q (in place; positions hold the bit-reversed-order input)
-template <int Q, int FIRST>
+template <int Q, int FIRST, bool LAZY_OUT = false>
 __device__ __forceinline__ void dit_base(uint32_t* v) {
 #pragma unroll
   for (int s = FIRST; s <= Q; s++) {
@@ -154,17 +178,21 @@ __device__ __forceinline__ void dit_base(uint32_t* v) {
     for (int blk = 0; blk < (1 << Q); blk += 2 * half) {
 #pragma unroll
       for (int j = 0; j < half; j++) {
-        uint32_t a = v[blk + j];
-        uint32_t b = v[blk + j + half];
-        if (j != 0) b = fp_mul(b, c_w16[j << (4 - s)]);
-        v[blk + j] = fp_add(a, b);
-        v[blk + j + half] = fp_sub(a, b);
+        const int lo = blk + j, hi = blk + j + half;
+        uint32_t a = v[lo];
+        uint32_t b = v[hi];
+        if (j != 0) b = mul_shoup(b, c_w16p[j << (4 - s)], c_w16s[j << (4 - s)]);
+        // position p of the next layer is a multiplied `b` input iff it lies in the upper half of its block, off the block's first column
+        const bool lazy_lo = s == Q ? LAZY_OUT : ((lo & (4 * half - 1)) >= 2 * half && (lo & (2 * half - 1)) != 0);
+        const bool lazy_hi = s == Q ? LAZY_OUT : ((hi & (4 * half - 1)) >= 2 * half && (hi & (2 * half - 1)) != 0);
+        v[lo] = lazy_lo ? a + b : fp_add(a, b);
+        v[hi] = lazy_hi ? a - b + P : fp_sub(a, b);
       }
     }
   }
 }
 // inverse: decimation in frequency, layers Q..1, inverse twiddles (natural in -> bit-reversed out)
-template <int Q>
+template <int Q, bool LAZY_OUT = false>
 __device__ __forceinline__ void dif_base(uint32_t* v) {
 #pragma unroll
   for (int s = Q; s >= 1; s--) {
@@ -175,9 +203,10 @@ __device__ __forceinline__ void dif_base(uint32_t* v) {
       for (int j = 0; j < half; j++) {
         uint32_t a = v[blk + j];
         uint32_t b = v[blk + j + half];
-        v[blk + j] = fp_add(a, b);
-        uint32_t d = fp_sub(a, b);
-        v[blk + j + half] = j != 0 ? fp_mul(d, c_w16i[j << (4 - s)]) : d;
+        const bool lazy = s == 1 && LAZY_OUT;
+        v[blk + j] = lazy ? a + b : fp_add(a, b);
+        if (j != 0) v[blk + j + half] = mul_shoup(a - b + P, c_w16ip[j << (4 - s)], c_w16is[j << (4 - s)]);
+        else v[blk + j + half] = lazy ? a - b + P : fp_sub(a, b);
       }
     }
   }

@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(BigPlan<R>::THREADS, BigPlan<R>::MINB) ntt_big
         ld16(v, a.in + (grow << R) + 16 * sr);
       }
       ld16(tw, a.gt[0] + ((16 * sr) & M));
-      dit_base<4, FIRST>(v);
+      dit_base<4, FIRST, true>(v);  // outputs in [0, 2P): the twist product below reduces them
       uint32_t* dst = sm + rl * PL::PITCH + 17 * sr;
 #pragma unroll
       for (int j = 0; j < 16; j++) dst[j] = fp_mul(v[j], tw[j]);
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(BigPlan<R>::THREADS, BigPlan<R>::MINB) ntt_big
       for (int j = 0; j < 16; j++) tw[j] = __ldg(twp + (j << LO));
 #pragma unroll
       for (int j = 0; j < 16; j++) v[j] = base[j * SJ];
-      dit_base<4, 1>(v);
+      dit_base<4, 1, true>(v);
 #pragma unroll
       for (int j = 0; j < 16; j++) base[j * SJ] = fp_mul(v[j], tw[j]);
     }
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(BigPlan<R>::THREADS, BigPlan<R>::MINB) ntt_big
       uint32_t v[1 << Q];
 #pragma unroll
       for (int j = 0; j < (1 << Q); j++) v[j] = base[j * SJ];
-      dit_base<Q, 1>(v);
+      dit_base<Q, 1, true>(v);  // [0, 2P) words between the passes: the strided pass multiplies by its pass twist first
       uint32_t* dst = a.out + ((row0 + rl) << R) + low;
 #pragma unroll
       for (int j = 0; j < (1 << Q); j++) dst[(size_t)j << LO] = v[j];
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(BigPlan<R>::THREADS, BigPlan<R>::MINB) ntt_big
       uint32_t v[1 << Q];
 #pragma unroll
       for (int j = 0; j < (1 << Q); j++) v[j] = src[(size_t)j << LO];
-      dif_base<Q>(v);
+      dif_base<Q, true>(v);
       uint32_t* base = sm + rl * PL::PITCH + low + (low >> 4);
 #pragma unroll
       for (int j = 0; j < (1 << Q); j++) base[j * SJ] = v[j];
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(BigPlan<R>::THREADS, BigPlan<R>::MINB) ntt_big
       for (int j = 0; j < 16; j++) tw[j] = __ldg(twp + (j << LO));
 #pragma unroll
       for (int j = 0; j < 16; j++) v[j] = fp_mul(base[j * SJ], tw[j]);
-      dif_base<4>(v);
+      dif_base<4, true>(v);
 #pragma unroll
       for (int j = 0; j < 16; j++) base[j * SJ] = v[j];
     }
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(BigPlan<R>::THREADS, BigPlan<R>::MINB) ntt_big
       const uint32_t* src = sm + rl * PL::PITCH + 17 * sr;
 #pragma unroll
       for (int j = 0; j < 16; j++) v[j] = fp_mul(src[j], tw[j]);
-      dif_base<4>(v);
+      dif_base<4, true>(v);
       if (a.scale_tab) {
         ld16(tw, a.scale_tab + ((uint32_t)g0 & nmask));
 #pragma unroll
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__((LANES << R) / 32, LANES == 16 ? 2 : 1) ntt_bi
         }
 #pragma unroll
         for (int j = 0; j < 16; j++) v[j] = fp_mul(v[j], tw[j]);
-        dit_base<4, 1>(v);
+        dit_base<4, 1, true>(v);
         const uint32_t* g0 = a.gt[0] + ((16 * sl) & M);
         uint32_t* dst = sm + (17 * sl) * LANES + l;
 #pragma unroll
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__((LANES << R) / 32, LANES == 16 ? 2 : 1) ntt_bi
         uint32_t v[16];
 #pragma unroll
         for (int j = 0; j < 16; j++) v[j] = base[j * SJ];
-        dit_base<4, 1>(v);
+        dit_base<4, 1, true>(v);
 #pragma unroll
         for (int j = 0; j < 16; j++) base[j * SJ] = fp_mul(v[j], __ldg(twp + (j << LO)));
       }
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__((LANES << R) / 32, LANES == 16 ? 2 : 1) ntt_bi
         uint32_t v[1 << Q];
 #pragma unroll
         for (int j = 0; j < (1 << Q); j++) v[j] = in[(size_t)(low + (j << LO)) << s_lo];
-        dif_base<Q>(v);
+        dif_base<Q, true>(v);
         uint32_t* base = sm + (low + (low >> 4)) * LANES + l;
 #pragma unroll
         for (int j = 0; j < (1 << Q); j++) base[j * SJ] = v[j];
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__((LANES << R) / 32, LANES == 16 ? 2 : 1) ntt_bi
         uint32_t v[16];
 #pragma unroll
         for (int j = 0; j < 16; j++) v[j] = fp_mul(base[j * SJ], __ldg(twp + (j << LO)));
-        dif_base<4>(v);
+        dif_base<4, true>(v);
 #pragma unroll
         for (int j = 0; j < 16; j++) base[j * SJ] = v[j];
       }
@@ -339,7 +339,7 @@ __global__ void __launch_bounds__((LANES << R) / 32, LANES == 16 ? 2 : 1) ntt_bi
         for (int j = 0; j < 16; j++) tw[j] = __ldg(pt + ((size_t)(16 * sl + j) << s_lo));
 #pragma unroll
         for (int j = 0; j < 16; j++) v[j] = fp_mul(src[j * LANES], __ldg(g0 + j));
-        dif_base<4>(v);
+        dif_base<4, true>(v);
 #pragma unroll
         for (int j = 0; j < 16; j++) out[(size_t)(16 * sl + j) << s_lo] = fp_mul(v[j], tw[j]);
       }
