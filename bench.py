@@ -153,6 +153,9 @@ def cpu_reference_run(steps: int, warmup: int, circuit: str = "rv32im_scale"):
     O.build()
     sc = named_circuit(circuit)
     oc = O.Circuit(sc.blob)
+    # libgomp reads OMP_NUM_THREADS when it is first loaded -- inside the GPU arm torch has loaded it long before, so the
+    # variable alone left that leg on another thread count than the reference arm (round 1: 64 vs 16 on the same box)
+    O.lib().or_set_num_threads(usable_cpus())
     cores = int(O.lib().or_num_threads())
     po2 = int(os.environ.get("B2Z_REF_PO2", str(CPU_SAMPLE_PO2)))  # (tests shrink it)
 

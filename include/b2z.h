@@ -137,17 +137,14 @@ b2z_err b2z_witgen(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, uint32_t* c
 b2z_err b2z_prove_segment_device(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, const uint32_t* code_dev,
                                  const uint32_t* data_dev, const uint32_t* globals_host, const uint32_t* accum_noise_dev,
                                  size_t zk_rows, uint32_t* seal_host, size_t* seal_words);
-/* Host buffers in, seal out: H2D of the witness and D2H of the seal happen inside the call (pageable or pinned sources,
- * see below).  A witness that does not satisfy the circuit returns an error. */
-b2z_err b2z_prove_segment(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, const uint32_t* code_host, const uint32_t* data_host,
-                          const uint32_t* globals_host, const uint32_t* accum_noise_host, size_t zk_rows, uint32_t* seal_host,
-                          size_t* seal_words);
 /* Host buffers in, seal out: H2D of the witness and D2H of the seal happen inside the call, the upload overlapped with
  * the commits.  Pinned buffers (cudaMallocHost / cudaHostRegister) are copied directly; PAGEABLE buffers (a Rust
  * Vec<u32>, a numpy array) are detected and staged through a pinned ring by helper threads, so both overlap.
- * An unsatisfied witness (non-zero DEEP remainder) is an ERROR, not a seal. */
-/* (b2z_prove_segment is declared above) */
-
+ * A witness that does not satisfy the circuit is an ERROR, not a seal (check-polynomial degree test + exact DEEP
+ * divisions); so is it for b2z_prove_segment_device. */
+b2z_err b2z_prove_segment(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, const uint32_t* code_host, const uint32_t* data_host,
+                          const uint32_t* globals_host, const uint32_t* accum_noise_host, size_t zk_rows, uint32_t* seal_host,
+                          size_t* seal_words);
 /* Control roots (risc0: the control-ID table): the Merkle root that the commitment of a program's code group has at a
  * given po2.  verify/mod.rs check_code(po2, code_root) binds a seal to the program -- the check behind
  * receipt.verify(image_id), /root/reference crates/host/src/bin/cli.rs:103.  b2z_compute_control_root derives it on the

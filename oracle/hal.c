@@ -12,6 +12,8 @@
 #include <string.h>
 
 int or_num_threads(void) { return omp_get_max_threads(); }
+/* the OpenMP runtime reads OMP_NUM_THREADS when it is first loaded (torch loads it long before the oracle): set it explicitly */
+void or_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 void or_free(void *p) { free(p); }
 
 /* twiddle table w^0..w^(n/2-1) */

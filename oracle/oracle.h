@@ -107,6 +107,7 @@ size_t or_prove_segment(const or_circuit *c, unsigned po2, const fp *code, const
 int or_verify_segment(const or_circuit *c, const uint32_t *seal, size_t seal_words);
 void or_free(void *p);
 int or_num_threads(void);
+void or_set_num_threads(int n);
 
 #ifdef __cplusplus
 }

@@ -22,6 +22,7 @@ double probe_sbox(double s, double rc) { return p2f_sbox_rc(s, rc); }
 double probe_from_mont(unsigned x) { return p2f_from_mont(x); }
 unsigned probe_to_mont(double x) { return p2f_to_mont(x); }
 void probe_m_ext(double* s) { p2f_m_ext(s); }
+double probe_red(double x) { return p2f_red(x); }
 }
 """
 
@@ -42,6 +43,8 @@ def probe(tmp_path_factory):
     L.probe_from_mont.argtypes = [C.c_uint]
     L.probe_to_mont.restype = C.c_uint
     L.probe_to_mont.argtypes = [C.c_double]
+    L.probe_red.restype = C.c_double
+    L.probe_red.argtypes = [C.c_double]
     return L
 
 
@@ -91,3 +94,50 @@ def test_external_layer_matches_the_matrix(probe):
         probe.probe_m_ext(buf)
         want = big.dot(np.array(s, dtype=object))
         assert [int(v) for v in buf] == list(want)
+
+
+def test_interval_propagation_proves_the_envelope():
+    """tests/cpp/f64_bounds.cpp compiles the REAL header with `double` replaced by a magnitude-tracking type and the two
+    exactness-critical primitives replaced by their contracts: one abstract run visits every call site of the permutation,
+    the Montgomery conversions and the carried-cell reduction, and proves (a) every linear-layer add / fma has integer
+    operands and a result below 2^53, (b) every p2f_mm call satisfies |a b| / P + 1 < 2^49, (c) every p2f_red input is
+    below 2^52.  The bounds depend only on the input bounds, so this covers all inputs -- not a sample."""
+    import json
+    import tempfile
+    exe = os.path.join(tempfile.mkdtemp(), "f64_bounds")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-o", exe, os.path.join(ROOT, "tests", "cpp", "f64_bounds.cpp")])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    rep = json.loads(out.stdout)
+    assert rep["violations"] == 0
+    assert rep["cell_out_bound_log2"] < 38 and rep["max_linear_value_log2"] < 53 and rep["max_p2f_mm_quotient_log2"] < 49
+    # the numeric lemma tests below must cover at least the operand range the proof found
+    assert rep["max_p2f_mm_quotient_log2"] < 47
+
+
+def test_primitive_contracts_on_adversarial_operands(probe):
+    """Lemma L1 / L2 of tests/cpp/f64_bounds.cpp at and beyond the largest operands the proof found (quotients up to 2^47,
+    i.e. |a b| up to 2^78), aimed at the rounding boundary: products within a few units of (q + 1/2) P."""
+    rng = random.Random(99)
+    n_hard = 0
+    for _ in range(20000):
+        ea = rng.randrange(20, 42)
+        a = rng.randrange(1 << (ea - 1), 1 << ea) * rng.choice((1, -1))
+        q = rng.randrange(1 << 30, 1 << 47)
+        target = q * P + P // 2 + rng.randrange(-3, 4)  # a b ~ (q + 1/2) P: the worst case for the rounded quotient
+        b = target // a + rng.randrange(-1, 2)
+        if abs(b) >= 1 << 40 or abs(a * b) // P + 1 >= 1 << 49:
+            continue
+        n_hard += 1
+        r = probe.probe_mm(float(a), float(b))
+        assert r == int(r) and (int(r) - a * b) % P == 0 and abs(r) <= 0.75 * P, (a, b, r)
+    assert n_hard > 3000
+    for _ in range(20000):
+        x = rng.randrange(-(1 << 52) + 1, 1 << 52)
+        r = probe.probe_red(float(x))
+        assert r == int(r) and (int(r) - x) % P == 0 and abs(r) <= 0.51 * P, (x, r)
+    for q in [0, 1, -1, (1 << 21) - 1, -(1 << 21)]:
+        for d in (-1, 0, 1):
+            x = q * P + P // 2 + d
+            r = probe.probe_red(float(x))
+            assert (int(r) - x) % P == 0 and abs(r) <= 0.51 * P

@@ -307,8 +307,14 @@ def test_prove_session_receipts(hal, oracle):
             dc, dd, dn = h.copy_from(code), h.copy_from(data), h.copy_from(noise)
             keep += [dc, dd, dn]
             wit.append(dict(po2=po2, code=dc, data=dd, globals=glob, accum_noise=dn, zk_rows=zk, on_device=True))
-        else:
+        elif i == 1:  # pageable host memory: staged upload inside the call
             wit.append(dict(po2=po2, code=code, data=data, globals=glob, accum_noise=noise, zk_rows=zk, on_device=False))
+        else:         # pinned host memory: the worker prefetches this witness while it proves its previous segment
+            import torch
+            pc, pd, pn = (torch.from_numpy(x.view(np.int32)).pin_memory() for x in (code, data, noise))
+            keep += [pc, pd, pn]
+            pinned_data3 = pd
+            wit.append(dict(po2=po2, code=pc.data_ptr(), data=pd.data_ptr(), globals=glob, accum_noise=pn.data_ptr(), zk_rows=zk, on_device=False))
     sess.set_control_root(po2, oc.control_roots[po2])
     r = sess.prove(wit, journal=b"blockhash")
     assert r.n_segments == 5 and r.journal == b"blockhash"
@@ -321,7 +327,7 @@ def test_prove_session_receipts(hal, oracle):
     assert sess.circuit.verify_receipt(r2, image_id) == (0, 0)
     # a violated constraint in segment 3 fails the whole session and names the segment
     derived = [col for col in range(sc.w_data) if sc.blob[-sc.w_data:][col] == 2]
-    bad = wit[3]["data"].copy()
+    bad = pinned_data3.numpy().view(np.uint32).copy()  # segment 3's (pinned) data columns
     bad[derived[0] * (1 << po2) + 7] ^= 1
     wit_bad = list(wit)
     wit_bad[3] = dict(wit[3], data=bad)

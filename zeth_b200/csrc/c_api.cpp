@@ -69,6 +69,7 @@ b2z_err b2z_destroy(b2z_ctx* ctx) {
     cudaEventDestroy(pr.second);
   }
   for (auto e : ctx->h2d_events) cudaEventDestroy(e);
+  for (auto e : ctx->event_pool) cudaEventDestroy(e);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
   if (ctx->aux_fork) cudaEventDestroy(ctx->aux_fork);

@@ -254,6 +254,18 @@ __device__ __forceinline__ u32 fsub(u32 a, u32 b) { u32 r = a - b; return min(r,
 __device__ __forceinline__ u32 fmul(u32 a, u32 b) {
   u64 t = (u64)a * b; u32 m = (u32)t * PINV; u32 u = __umulhi(m, P); u32 r = (u32)(t >> 32) - u; return min(r, r + P);
 }
+// sums of up to four products reduced ONCE: every product of two canonical words is < P^2 and 4 P^2 < 2^64, so the terms are
+// accumulated in 64 bits (one IMAD.WIDE each) and the sum x is brought to x * 2^-32 mod P by one Montgomery step
+__device__ __forceinline__ u32 red64(u64 x) {
+  u32 hi = (u32)(x >> 32), lo = (u32)x;
+  hi = min(hi, hi - P); hi = min(hi, hi - P);  // hi < 2^32 < 3 P -> hi < P
+  u32 m = lo * PINV; u32 u = __umulhi(m, P); u32 r = hi - u; return min(r, r + P);
+}
+__device__ __forceinline__ u32 dot2(u32 a0, u32 b0, u32 a1, u32 b1) { return red64((u64)a0 * b0 + (u64)a1 * b1); }
+__device__ __forceinline__ u32 dot3(u32 a0, u32 b0, u32 a1, u32 b1, u32 a2, u32 b2) { return red64((u64)a0 * b0 + (u64)a1 * b1 + (u64)a2 * b2); }
+__device__ __forceinline__ u32 dot4(u32 a0, u32 b0, u32 a1, u32 b1, u32 a2, u32 b2, u32 a3, u32 b3) {
+  return red64((u64)a0 * b0 + (u64)a1 * b1 + (u64)a2 * b2 + (u64)a3 * b3);
+}
 struct E { u32 a, b, c, d; };
 __device__ __forceinline__ E emake(u32 a, u32 b, u32 c, u32 d) { E r; r.a = a; r.b = b; r.c = c; r.d = d; return r; }
 __device__ __forceinline__ E eadd(E x, E y) { return emake(fadd(x.a, y.a), fadd(x.b, y.b), fadd(x.c, y.c), fadd(x.d, y.d)); }
@@ -328,6 +340,21 @@ struct Emitter {
       Stmt st{id, expr, {}};
       if (a && a->tid >= 0) st.uses.push_back((unsigned)a->tid);
       if (b && b->tid >= 0) st.uses.push_back((unsigned)b->tid);
+      stmts->push_back(st);
+    } else {
+      *o << "  const u32 " << n << " = " << expr << ";\n";
+    }
+    Opd r = named(n);
+    r.tid = (int)id;
+    return r;
+  }
+  Opd emit_n(const std::string& expr, const std::vector<Opd>& ops) {
+    unsigned id = tmp++;
+    std::string n = "t" + std::to_string(id);
+    if (stmts) {
+      Stmt st{id, expr, {}};
+      for (const auto& x : ops)
+        if (x.tid >= 0) st.uses.push_back((unsigned)x.tid);
       stmts->push_back(st);
     } else {
       *o << "  const u32 " << n << " = " << expr << ";\n";
@@ -501,29 +528,82 @@ void circuit_codegen(b2z_circuit* c) {
     em.cp_name = cpn;
     em.kc_name = kcn;
     if (parts_m > 0) em.stmts = &stmts;
-    std::vector<Val> mixv;  // accumulated `tot` of every mix variable
+    // A mix variable = its accumulated `tot` plus up to three constraints not folded in yet.  Constraint values are base-field
+    // words, so a run of AndEqz steps adds pw[e] * val_e to each of the four components: four such terms are accumulated in
+    // 64 bits and reduced once (dot4, 10 instructions per component) instead of four products + four modular adds (28).
+    // B2Z_EVALCHECK_DOT=0 restores the term-by-term form.
+    struct MixAcc {
+      Val tot;
+      std::vector<std::pair<uint32_t, Opd>> pend;  // (exponent of poly_mix, base-field value)
+    };
+    const bool use_dot = !(getenv("B2Z_EVALCHECK_DOT") && getenv("B2Z_EVALCHECK_DOT")[0] == '0');
+    std::vector<MixAcc> mixv;
+    auto flush = [&](MixAcc& m) {
+      if (m.pend.empty()) return;
+      for (int k = 0; k < 4; k++) {
+        std::string expr;
+        std::vector<Opd> ops;
+        size_t nterm = 0;
+        for (auto& pr : m.pend) {
+          if (pr.first == 0) continue;  // alpha^0 = 1: handled below
+          expr += (nterm ? ", " : "") + kcn + ".pw[" + std::to_string(4 * pr.first + k) + "], " + pr.second.str();
+          ops.push_back(pr.second);
+          nterm++;
+        }
+        Opd d;
+        bool have = false;
+        if (nterm == 1) {
+          d = em.emit_n("fmul(" + expr + ")", ops);
+          have = true;
+        } else if (nterm >= 2) {
+          d = em.emit_n("dot" + std::to_string(nterm) + "(" + expr + ")", ops);
+          have = true;
+        }
+        if (have) m.tot.c[k] = em.s_add(m.tot.c[k], d);
+      }
+      for (auto& pr : m.pend)
+        if (pr.first == 0) m.tot.c[0] = em.s_add(m.tot.c[0], pr.second);
+      m.pend.clear();
+    };
     for (const auto& s : c->steps) {
       switch (s.op) {
         case OP_TRUE: {
-          Val z;
-          z.ext = true;
+          MixAcc z;
+          z.tot.ext = true;
           mixv.push_back(z);  // all four components constant 0
         } break;
         case OP_AND_EQZ: {
-          Val term = em.v_mul(pw_val(c->mix_exp[s.a], kcn), em.use(s.b));
-          mixv.push_back(em.v_add(mixv[s.a], term, false));
+          Val v = em.use(s.b);
+          MixAcc n = mixv[s.a];
+          if (use_dot && !v.ext && !v.c[0].is_const) {
+            n.pend.push_back({c->mix_exp[s.a], v.c[0]});
+            if (n.pend.size() == 4) flush(n);
+          } else {
+            flush(n);
+            Val term = em.v_mul(pw_val(c->mix_exp[s.a], kcn), v);
+            n.tot = em.v_add(n.tot, term, false);
+          }
+          mixv.push_back(n);
           cut_points.push_back(stmts.size());
         } break;
         case OP_AND_COND: {
-          Val inner = em.v_mul(mixv[s.c], em.use(s.b));
+          MixAcc chain = mixv[s.a], in = mixv[s.c];
+          flush(chain);
+          flush(in);
+          Val inner = em.v_mul(in.tot, em.use(s.b));
           Val term = em.v_mul(inner, pw_val(c->mix_exp[s.a], kcn));
-          mixv.push_back(em.v_add(mixv[s.a], term, false));
+          chain.tot = em.v_add(chain.tot, term, false);
+          mixv.push_back(chain);
           cut_points.push_back(stmts.size());
         } break;
         default: em.step(s); break;
       }
     }
-    result = mixv[c->ret];
+    {
+      MixAcc r = mixv[c->ret];
+      flush(r);
+      result = r.tot;
+    }
   }
   // parts mode reads its tables from module __constant__ memory (ccp / ckc): the two structs must NOT also travel as kernel
   // parameters (a program of the rv32im size class has ~45 KB of poly_mix powers; the parameter space is 32 KB)
@@ -534,9 +614,10 @@ void circuit_codegen(b2z_circuit* c) {
   // B2Z_EVALCHECK_THREADS = T (parts mode, one point per thread): CTA size.  With T > 128 the CTA's warps are held together by a
   // barrier after every part, so a part's instructions are fetched from L2 once per CTA and stay in the SM's instruction
   // cache while all of its warps run them -- a straight-line program of megabytes otherwise streams once per WARP.
-  int cta_threads = 128;
+  // Measured on B200 (rv32im-scale program, 27 542 steps, po2 20): T = 128 (no barrier) 52.9 ms, 256: 44.4, 512: 44.6, 1024: 46.6.
+  int cta_threads = 256;
   if (const char* e = getenv("B2Z_EVALCHECK_THREADS")) cta_threads = atoi(e);
-  if (cta_threads != 256 && cta_threads != 512 && cta_threads != 1024) cta_threads = 128;
+  if (cta_threads != 128 && cta_threads != 512 && cta_threads != 1024) cta_threads = 256;
   if (parts_m <= 0 || points_k != 1) cta_threads = 128;
   c->eval_threads = (unsigned)cta_threads;
   const bool cta_sync = cta_threads > 128;

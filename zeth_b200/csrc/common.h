@@ -43,6 +43,7 @@ struct b2z_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;          // host->device witness uploads overlapped with compute (b2z_prove_segment)
   std::vector<cudaEvent_t> h2d_events;
+  std::vector<cudaEvent_t> event_pool;         // recycled timing-disabled events of the witness uploads
   // pinned staging ring for PAGEABLE host witnesses (b2z_prove_segment): slots of 16 MB, one drain event per slot
   char* stage_ring = nullptr;
   std::vector<cudaEvent_t> stage_events;

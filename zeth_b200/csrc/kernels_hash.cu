@@ -80,10 +80,7 @@ __global__ void __launch_bounds__(THREADS, MINB) hash_rows_kernel(uint32_t* __re
 // balances their different speeds.  sched[0] = tile counter, sched[1 + smid] = CTA arrival counter of that SM.
 constexpr int HASH_SCHED_WORDS = 1 + 512;
 
-__device__ __forceinline__ double p2f_reduce(double x) {  // |x| < 2^38 -> (-0.51 P, 0.51 P)
-  double q = __dadd_rn(__fma_rn(x, F64_INVP, F64_MAGIC), -F64_MAGIC);
-  return __fma_rn(q, -F64_P, x);
-}
+__device__ __forceinline__ double p2f_reduce(double x) { return p2f_red(x); }  // |x| < 2^38 -> (-0.51 P, 0.51 P)
 
 // both row routines keep a single call site of their permutation (tail columns are predicated loads of 0).
 // The guarded load is spelled in PTX: left to itself the compiler widens the guard to 64 bits and rebuilds every

@@ -38,7 +38,11 @@ constexpr double F64_RINV_OVER_P = 943718400.0 / 2013265921.0;
 constexpr double F64_RMOD = 268435454.0;            // R mod P (plain residue -> Montgomery word)
 constexpr double F64_RMOD_OVER_P = 268435454.0 / 2013265921.0;
 
-#if defined(__CUDA_ARCH__)
+// (tests/cpp/f64_bounds.cpp re-includes this header with `double` replaced by a magnitude-tracking type and with the three
+// macros and the two exactness-critical primitives p2f_mm / p2f_red hooked: it PROVES the envelope claims made below)
+#if defined(B2Z_DADD)
+// arithmetic supplied by the including translation unit
+#elif defined(__CUDA_ARCH__)
 #define B2Z_DADD(a, b) __dadd_rn((a), (b))
 #define B2Z_DMUL(a, b) __dmul_rn((a), (b))
 #define B2Z_DFMA(a, b, c) __fma_rn((a), (b), (c))
@@ -52,6 +56,7 @@ constexpr double F64_RMOD_OVER_P = 268435454.0 / 2013265921.0;
 //   q = rint(a b / P)                      (|q| < 2^49, off from the true nearest integer by < 0.2)
 //   u = a b - q (P - 1)   exactly: one fma, the true value r + q is an integer below 2^50
 //   r = u - q             in (-0.7 P, 0.7 P)
+#if !defined(B2Z_P2F_PRIMS_HOOKED)
 B2Z_HD double p2f_mm(double a, double a_over_p, double b) {
   double t = B2Z_DFMA(a_over_p, b, F64_MAGIC);
   double q = B2Z_DADD(t, -F64_MAGIC);
@@ -59,6 +64,12 @@ B2Z_HD double p2f_mm(double a, double a_over_p, double b) {
   double u = B2Z_DFMA(a, b, c);
   return B2Z_DADD(u, -q);
 }
+// x mod P for an integer |x| < 2^52: q = rint(x / P) has |q| < 2^22, so q * P is exact and one fma finishes; result in (-0.51 P, 0.51 P)
+B2Z_HD double p2f_red(double x) {
+  double q = B2Z_DADD(B2Z_DFMA(x, F64_INVP, F64_MAGIC), -F64_MAGIC);
+  return B2Z_DFMA(q, -F64_P, x);
+}
+#endif
 
 // (s + rc)^7: 24 FP64 operations
 B2Z_HD double p2f_sbox_rc(double s, double rc) {
@@ -115,8 +126,7 @@ B2Z_HD void p2f_m_int(double* s, const P2ConstsF64& k) {
   for (int i = 0; i < 6; i++) t4[i] = B2Z_DADD(t8[2 * i], t8[2 * i + 1]);
   double tot = B2Z_DADD(B2Z_DADD(B2Z_DADD(t4[0], t4[1]), B2Z_DADD(t4[2], t4[3])), B2Z_DADD(t4[4], t4[5]));
   // tot mod P: |tot| < 2^37, so q * P is exact and one fma finishes the reduction
-  double tq = B2Z_DADD(B2Z_DFMA(tot, F64_INVP, F64_MAGIC), -F64_MAGIC);
-  double totr = B2Z_DFMA(tq, -F64_P, tot);
+  double totr = p2f_red(tot);
 #pragma unroll
   for (int i = 0; i < P2_CELLS; i++) s[i] = B2Z_DADD(p2f_mm(k.diag[i], k.diag_over_p[i], s[i]), totr);
 }

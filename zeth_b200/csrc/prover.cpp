@@ -14,6 +14,7 @@
 #include <condition_variable>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <thread>
 
@@ -646,64 +647,148 @@ void staged_upload_worker(b2z_ctx* ctx, std::vector<UploadChunk>* chunks, std::a
 }
 }  // namespace
 
-b2z_err prove_segment_host(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, const uint32_t* code_host, const uint32_t* data_host,
-                           const uint32_t* globals_host, const uint32_t* accum_noise_host, size_t zk_rows, uint32_t* seal_host,
-                           size_t* seal_words) {
+// A witness on its way to the device (pinned sources): device buffers + the events its chunks are signalled on.  Begun early
+// (the session prefetches segment i + 1 while segment i is being proved), consumed by prove_segment_uploaded.
+struct HostUpload {
+  uint32_t *code = nullptr, *data = nullptr, *noise = nullptr;
+  WitnessReady ready;
+  std::vector<cudaEvent_t> events;
+};
+static cudaEvent_t take_event(b2z_ctx* ctx) {
+  if (!ctx->event_pool.empty()) {
+    cudaEvent_t e = ctx->event_pool.back();
+    ctx->event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+  return e;
+}
+void host_upload_discard(b2z_ctx* ctx, HostUpload* up) {
+  if (!up) return;
+  cudaStreamSynchronize(ctx->copy_stream);
+  for (void* p : {(void*)up->code, (void*)up->data, (void*)up->noise})
+    if (p) cudaFreeAsync(p, ctx->stream);
+  for (auto e : up->events) ctx->event_pool.push_back(e);
+  delete up;
+}
+// upload plan in consumption order: code chunks (4 columns: the first compute starts after ~1 ms of PCIe), data chunks (32
+// columns = two sponge blocks), accum noise
+static void plan_chunks(const b2z_circuit* c, unsigned po2, size_t zk_rows, uint32_t* code, uint32_t* data, uint32_t* noise, const uint32_t* code_host,
+                        const uint32_t* data_host, const uint32_t* noise_host, WitnessReady& ready, std::vector<UploadChunk>& chunks,
+                        const std::function<cudaEvent_t()>& next_event) {
+  const size_t n = (size_t)1 << po2;
+  const size_t wa = c->group_size[0], wc = c->group_size[1], wd = c->group_size[2];
+  ready.chunk_cols = 32;
+  ready.code_chunk_cols = 4;
+  const size_t nchunks = (wd + ready.chunk_cols - 1) / ready.chunk_cols, ncode = (wc + ready.code_chunk_cols - 1) / ready.code_chunk_cols;
+  for (size_t k = 0; k < ncode; k++) {
+    size_t c0 = k * ready.code_chunk_cols, cols = wc - c0 < ready.code_chunk_cols ? wc - c0 : ready.code_chunk_cols;
+    cudaEvent_t e = next_event();
+    chunks.emplace_back((char*)(code + c0 * n), (const char*)(code_host + c0 * n), 4 * cols * n, e);
+    ready.code_chunks.push_back(e);
+  }
+  for (size_t k = 0; k < nchunks; k++) {
+    size_t c0 = k * ready.chunk_cols, cols = wd - c0 < ready.chunk_cols ? wd - c0 : ready.chunk_cols;
+    cudaEvent_t e = next_event();
+    chunks.emplace_back((char*)(data + c0 * n), (const char*)(data_host + c0 * n), 4 * cols * n, e);
+    ready.data_chunks.push_back(e);
+  }
+  ready.noise = next_event();
+  chunks.emplace_back((char*)noise, (const char*)noise_host, 4 * wa * zk_rows, ready.noise);
+  ready.code_gate0 = 0;
+  ready.data_gate0 = ncode;
+  ready.noise_gate = ncode + nchunks;
+}
+static bool sources_pinned(const b2z_circuit* c, unsigned po2, size_t zk_rows, const uint32_t* code_host, const uint32_t* data_host,
+                           const uint32_t* noise_host) {
+  (void)po2;
+  const size_t wa = c->group_size[0], wc = c->group_size[1], wd = c->group_size[2];
+  return (wc == 0 || host_pointer_is_pinned(code_host)) && (wd == 0 || host_pointer_is_pinned(data_host)) &&
+         (wa * zk_rows == 0 || host_pointer_is_pinned(noise_host));
+}
+
+// Begin the upload of a PINNED witness: every copy and event is enqueued now; *out stays NULL for pageable sources.
+b2z_err host_upload_begin(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, const uint32_t* code_host, const uint32_t* data_host,
+                          const uint32_t* accum_noise_host, size_t zk_rows, HostUpload** out) {
+  *out = nullptr;
   B2Z_REQUIRE(po2 >= 1 && po2 <= 24, "po2 out of range");
   const size_t n = (size_t)1 << po2;
   B2Z_REQUIRE(zk_rows < n, "zk_rows must be smaller than the trace");
+  if (!sources_pinned(c, po2, zk_rows, code_host, data_host, accum_noise_host)) return nullptr;
   const size_t wa = c->group_size[0], wc = c->group_size[1], wd = c->group_size[2];
   if (!ctx->copy_stream) B2Z_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-  WitnessReady ready;
-  ready.chunk_cols = 32;
-  ready.code_chunk_cols = 4;  // the very first transfer is the only one nothing can hide: keep it short
-  size_t nchunks = (wd + ready.chunk_cols - 1) / ready.chunk_cols;
-  size_t ncode = (wc + ready.code_chunk_cols - 1) / ready.code_chunk_cols;
-  while (ctx->h2d_events.size() < nchunks + ncode + 2) {
-    cudaEvent_t e;
-    B2Z_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    ctx->h2d_events.push_back(e);
+  HostUpload* up = new HostUpload();
+  auto fail = [&](b2z_err e) {
+    host_upload_discard(ctx, up);
+    return e;
+  };
+  if (cudaMallocAsync(&up->code, 4 * (wc * n + 1), ctx->stream) != cudaSuccess || cudaMallocAsync(&up->data, 4 * (wd * n + 1), ctx->stream) != cudaSuccess ||
+      cudaMallocAsync(&up->noise, 4 * (wa * zk_rows + 1), ctx->stream) != cudaSuccess)
+    return fail(set_error(std::string("witness buffers: ") + cudaGetErrorString(cudaGetLastError())));
+  // the copy stream may only touch the buffers once the (stream-ordered) allocations are visible
+  cudaEvent_t alloc_done = take_event(ctx);
+  up->events.push_back(alloc_done);
+  cudaEventRecord(alloc_done, ctx->stream);
+  cudaStreamWaitEvent(ctx->copy_stream, alloc_done, 0);
+  std::vector<UploadChunk> chunks;
+  plan_chunks(c, po2, zk_rows, up->code, up->data, up->noise, code_host, data_host, accum_noise_host, up->ready, chunks, [&] {
+    cudaEvent_t e = take_event(ctx);
+    up->events.push_back(e);
+    return e;
+  });
+  for (auto& ch : chunks) {
+    if (ch.bytes && cudaMemcpyAsync(ch.dst, ch.src, ch.bytes, cudaMemcpyHostToDevice, ctx->copy_stream) != cudaSuccess)
+      return fail(set_error(std::string("witness upload: ") + cudaGetErrorString(cudaGetLastError())));
+    cudaEventRecord(ch.event, ctx->copy_stream);
   }
+  *out = up;
+  return nullptr;
+}
+
+b2z_err prove_segment_uploaded(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, HostUpload* up, const uint32_t* globals_host, size_t zk_rows,
+                               uint32_t* seal_host, size_t* seal_words) {
+  ctx->last_upload_staged = false;
+  b2z_err err = prove_segment_device(ctx, c, po2, up->code, up->data, globals_host, up->noise, zk_rows, seal_host, seal_words, &up->ready);
+  host_upload_discard(ctx, up);
+  return err;
+}
+
+b2z_err prove_segment_host(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, const uint32_t* code_host, const uint32_t* data_host,
+                           const uint32_t* globals_host, const uint32_t* accum_noise_host, size_t zk_rows, uint32_t* seal_host,
+                           size_t* seal_words) {
+  HostUpload* up = nullptr;
+  B2Z_TRY(host_upload_begin(ctx, c, po2, code_host, data_host, accum_noise_host, zk_rows, &up));
+  if (up) return prove_segment_uploaded(ctx, c, po2, up, globals_host, zk_rows, seal_host, seal_words);
+  // pageable sources: staged through the pinned ring by helper threads
+  const size_t n = (size_t)1 << po2;
+  const size_t wa = c->group_size[0], wc = c->group_size[1], wd = c->group_size[2];
+  if (!ctx->copy_stream) B2Z_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  ctx->last_upload_staged = true;
   DevMem wit(ctx);  // released on every exit path
   uint32_t *code = nullptr, *data = nullptr, *noise = nullptr;
   B2Z_TRY(wit.alloc(&code, wc * n + 1));
   B2Z_TRY(wit.alloc(&data, wd * n + 1));
   B2Z_TRY(wit.alloc(&noise, wa * zk_rows + 1));
-  // the copy stream may only touch the buffers once the (stream-ordered) allocations are visible
-  cudaEvent_t alloc_done = ctx->h2d_events[nchunks + ncode + 1];
+  std::vector<cudaEvent_t> evs;
+  struct Return {
+    b2z_ctx* ctx;
+    std::vector<cudaEvent_t>& evs;
+    ~Return() {
+      for (auto e : evs) ctx->event_pool.push_back(e);
+    }
+  } ret{ctx, evs};
+  cudaEvent_t alloc_done = take_event(ctx);
+  evs.push_back(alloc_done);
   B2Z_CUDA(cudaEventRecord(alloc_done, ctx->stream));
   B2Z_CUDA(cudaStreamWaitEvent(ctx->copy_stream, alloc_done, 0));
-  // upload plan in consumption order: code chunks, data chunks, accum noise
+  WitnessReady ready;
   std::vector<UploadChunk> chunks;
-  for (size_t k = 0; k < ncode; k++) {
-    size_t c0 = k * ready.code_chunk_cols, cols = wc - c0 < ready.code_chunk_cols ? wc - c0 : ready.code_chunk_cols;
-    chunks.emplace_back((char*)(code + c0 * n), (const char*)(code_host + c0 * n), 4 * cols * n, ctx->h2d_events[nchunks + k]);
-    ready.code_chunks.push_back(ctx->h2d_events[nchunks + k]);
-  }
-  for (size_t k = 0; k < nchunks; k++) {
-    size_t c0 = k * ready.chunk_cols, cols = wd - c0 < ready.chunk_cols ? wd - c0 : ready.chunk_cols;
-    chunks.emplace_back((char*)(data + c0 * n), (const char*)(data_host + c0 * n), 4 * cols * n, ctx->h2d_events[k]);
-    ready.data_chunks.push_back(ctx->h2d_events[k]);
-  }
-  ready.noise = ctx->h2d_events[nchunks + ncode];
-  chunks.emplace_back((char*)noise, (const char*)accum_noise_host, 4 * wa * zk_rows, ready.noise);
-  ready.code_gate0 = 0;
-  ready.data_gate0 = ncode;
-  ready.noise_gate = ncode + nchunks;
-
-  const bool pinned = (wc == 0 || host_pointer_is_pinned(code_host)) && (wd == 0 || host_pointer_is_pinned(data_host)) &&
-                      (wa * zk_rows == 0 || host_pointer_is_pinned(accum_noise_host));
-  ctx->last_upload_staged = !pinned;
-  if (pinned) {
-    for (auto& ch : chunks) {
-      if (ch.bytes) B2Z_CUDA(cudaMemcpyAsync(ch.dst, ch.src, ch.bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
-      B2Z_CUDA(cudaEventRecord(ch.event, ctx->copy_stream));
-    }
-    b2z_err err = prove_segment_device(ctx, c, po2, code, data, globals_host, noise, zk_rows, seal_host, seal_words, &ready);
-    cudaStreamSynchronize(ctx->copy_stream);
-    return err;
-  }
-  // pageable sources: staged through the pinned ring by helper threads
+  plan_chunks(c, po2, zk_rows, code, data, noise, code_host, data_host, accum_noise_host, ready, chunks, [&] {
+    cudaEvent_t e = take_event(ctx);
+    evs.push_back(e);
+    return e;
+  });
   if (!ctx->stage_ring) {
     B2Z_CUDA(cudaMallocHost((void**)&ctx->stage_ring, STAGE_SLOTS * STAGE_PIECE_BYTES));
     for (size_t i = 0; i < STAGE_SLOTS; i++) {

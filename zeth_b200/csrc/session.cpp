@@ -30,6 +30,12 @@ b2z_err prove_segment_host(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, con
                            const uint32_t* globals_host, const uint32_t* accum_noise_host, size_t zk_rows, uint32_t* seal_host,
                            size_t* seal_words);
 int verify_segment(const b2z_circuit* c, const uint32_t* seal, size_t seal_words);
+struct HostUpload;
+b2z_err host_upload_begin(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, const uint32_t* code_host, const uint32_t* data_host,
+                          const uint32_t* accum_noise_host, size_t zk_rows, HostUpload** out);
+b2z_err prove_segment_uploaded(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, HostUpload* up, const uint32_t* globals_host, size_t zk_rows,
+                               uint32_t* seal_host, size_t* seal_words);
+void host_upload_discard(b2z_ctx* ctx, HostUpload* up);
 
 // digest naming (proof system, circuit): SegmentReceipt::verifier_parameters stand-in
 void verifier_parameters(const b2z_circuit* c, uint32_t* out8) {
@@ -340,16 +346,38 @@ b2z_err b2z_prove_session(b2z_session* s, const b2z_segment_input* segs, size_t 
   auto work = [&](size_t wi) {
     b2z_session::Worker& w = s->workers[wi];
     cudaSetDevice(s->device);
+    // the worker claims its NEXT segment early and starts that witness's upload (pinned host sources) before it proves the
+    // current one: PCIe runs decoupled from the commit phases, and two workers do not fall into upload-bound lockstep
+    auto begin = [&](size_t i, HostUpload** up) {
+      *up = nullptr;
+      if (i < n && !segs[i].on_device && !failed.load())
+        host_upload_begin(w.ctx, w.circuit, segs[i].po2, segs[i].code, segs[i].data, segs[i].accum_noise, segs[i].zk_rows, up);  // NULL on pageable sources / errors
+    };
+    size_t i_next = next.fetch_add(1);
+    HostUpload* up_next = nullptr;
+    begin(i_next, &up_next);
     for (;;) {
-      size_t i = next.fetch_add(1);
-      if (i >= n || failed.load()) return;
+      const size_t i = i_next;
+      HostUpload* up = up_next;
+      if (i >= n || failed.load()) {
+        host_upload_discard(w.ctx, up);
+        return;
+      }
+      i_next = next.fetch_add(1);
+      begin(i_next, &up_next);
       const b2z_segment_input& g = segs[i];
       b2z_err e = nullptr;
       auto ts = std::chrono::steady_clock::now();
       for (int attempt = 0; attempt < 2; attempt++) {  // one retry: a transient device error must not lose the session
         size_t sw = 0;
-        e = g.on_device ? prove_segment_device(w.ctx, w.circuit, g.po2, g.code, g.data, g.globals, g.accum_noise, g.zk_rows, seals[i].data(), &sw, nullptr)
-                        : prove_segment_host(w.ctx, w.circuit, g.po2, g.code, g.data, g.globals, g.accum_noise, g.zk_rows, seals[i].data(), &sw);
+        if (g.on_device) {
+          e = prove_segment_device(w.ctx, w.circuit, g.po2, g.code, g.data, g.globals, g.accum_noise, g.zk_rows, seals[i].data(), &sw, nullptr);
+        } else if (up) {
+          e = prove_segment_uploaded(w.ctx, w.circuit, g.po2, up, g.globals, g.zk_rows, seals[i].data(), &sw);
+          up = nullptr;
+        } else {
+          e = prove_segment_host(w.ctx, w.circuit, g.po2, g.code, g.data, g.globals, g.accum_noise, g.zk_rows, seals[i].data(), &sw);
+        }
         if (!e) break;
         // an unsatisfied witness is deterministic: retrying cannot help
         if (strstr(e, "does not satisfy")) break;
@@ -364,6 +392,7 @@ b2z_err b2z_prove_session(b2z_session* s, const b2z_segment_input* segs, size_t 
         std::lock_guard<std::mutex> lock(err_mutex);
         if (first_error.empty()) first_error = "segment " + std::to_string(g.index) + ": " + e;
         failed.store(true);
+        host_upload_discard(w.ctx, up_next);
         return;
       }
     }
