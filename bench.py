@@ -528,20 +528,8 @@ def run_block_workload(args):
         sampler.start()
 
     def gather(receipt, count_per_rank):
-        """every rank's seals -> rank 0, one all_gather of exact seal words from a pinned staging buffer"""
-        if world == 1:
-            return [receipt.seal(i) for i in range(receipt.n_segments)]
-        stage = torch.empty((count_per_rank, seal_words), dtype=torch.int32).pin_memory()
-        st = stage.numpy().view(np.uint32)
-        for i in range(receipt.n_segments):
-            st[i] = receipt.seal(i)
-        mine = stage.to(dev, non_blocking=True)
-        allg = torch.empty((world * count_per_rank, seal_words), dtype=torch.int32, device=dev)
-        dist.all_gather_into_tensor(allg, mine)
-        if rank != 0:
-            return None
-        host = allg.cpu().numpy().view(np.uint32)
-        return [host[(i % world) * count_per_rank + i // world] for i in range(world * count_per_rank)]
+        """every rank's seals -> rank 0: one all_gather of exact seal words from a pinned staging buffer (zeth_b200/shard.py)"""
+        return shard.all_gather_seals([receipt.seal(i) for i in range(receipt.n_segments)], count_per_rank, seal_words, dev)
 
     assert n_timed % world == 0, "K * segments-per-step must be a multiple of the number of GPUs"
     per_rank = n_timed // world

@@ -658,6 +658,7 @@ void circuit_codegen(b2z_circuit* c) {
     for (int k = 0; k < 4; k++)
       if (result.c[k].tid >= 0) last_use_part[(unsigned)result.c[k].tid] = FINAL;
     std::ostringstream main_body;
+    std::vector<std::vector<unsigned>> part_ins, part_outs;
     for (size_t p = 0; p + 1 < bounds.size(); p++) {
       std::vector<unsigned> ins, outs;
       std::map<unsigned, bool> seen;
@@ -669,6 +670,8 @@ void circuit_codegen(b2z_circuit* c) {
           }
         if (last_use_part.count(stmts[k].id) && last_use_part[stmts[k].id] > p) outs.push_back(stmts[k].id);
       }
+      part_ins.push_back(ins);
+      part_outs.push_back(outs);
       o << "struct PR" << p << " { u32 v[" << (outs.empty() ? 1 : outs.size()) << "]; };\n";
       o << "static __device__ __noinline__ PR" << p << " part" << p << "(" << ib_params;
       for (unsigned u : ins) o << ", u32 t" << u;
@@ -683,7 +686,66 @@ void circuit_codegen(b2z_circuit* c) {
       main_body << ");\n";
       for (size_t j = 0; j < outs.size(); j++) main_body << "  const u32 t" << outs[j] << " = r" << p << ".v[" << j << "];\n";
     }
-    if (points_k == 1) {
+    // B2Z_EVALCHECK_TILES = K > 1 (one point per thread, synchronised CTAs): a CTA owns K consecutive tiles of T points and runs
+    // EVERY part over all K tiles before it moves on, so a part's instructions are fetched once per K * T points and execute out
+    // of the instruction cache K - 1 times out of K (ncu on the rv32im-scale program with K = 1: `no_instruction` is the top
+    // stall, issue 55 %).  The few values that are live across parts (the constraint accumulators, pending dot terms) live in
+    // shared memory, [slot][tile][thread], instead of registers -- K points per thread at no register cost (round 1's
+    // K-points-per-thread emission lost exactly because of the registers).
+    int tiles_k = 1;  // measured: K = 1 35.8 ms, K = 2 42.2, K = 3 42.2, K = 4 49.4 (rv32im-scale, po2 20) -- a negative result, kept as a knob
+    if (const char* e = getenv("B2Z_EVALCHECK_TILES")) tiles_k = atoi(e);
+    if (tiles_k < 1 || tiles_k > 16 || !cta_sync || points_k != 1) tiles_k = 1;
+    c->eval_tiles = (unsigned)tiles_k;
+    c->eval_smem_bytes = 0;
+    if (tiles_k > 1) {
+      // slot allocation by liveness: a temporary occupies a slot from its defining part to its last reading part
+      const size_t np = bounds.size() - 1;
+      std::map<unsigned, unsigned> slot_of;
+      std::vector<size_t> free_at;  // per slot: the first part in which it may be reused
+      for (size_t p = 0; p < np; p++)
+        for (unsigned tid : part_outs[p]) {
+          const size_t last = last_use_part[tid];  // a later part, or FINAL
+          unsigned sidx = (unsigned)free_at.size();
+          for (unsigned q = 0; q < free_at.size(); q++)
+            if (free_at[q] <= p) {
+              sidx = q;
+              break;
+            }
+          if (sidx == free_at.size()) free_at.push_back(0);
+          free_at[sidx] = last == FINAL ? (size_t)-1 : last + 1;  // readable through its last use
+          slot_of[tid] = sidx;
+        }
+      const size_t n_slots = free_at.size() ? free_at.size() : 1;
+      c->eval_smem_bytes = 4 * n_slots * (size_t)tiles_k * (size_t)cta_threads;
+      const int mb = std::max(1, min_blocks * 128 / cta_threads);
+      auto slot = [&](unsigned tid) { return "st[(" + std::to_string(slot_of[tid]) + " * " + std::to_string(tiles_k) + " + k) * " + std::to_string(cta_threads) + " + threadIdx.x]"; };
+      o << "// " << n_slots << " shared-memory slots hold the values that cross part boundaries\n";
+      o << "extern \"C\" __global__ void __launch_bounds__(" << cta_threads << ", " << mb << ") b2z_eval_check(" << kernel_head_params << ") {\n";
+      o << "  extern __shared__ u32 st[];\n  const u64 domain = mask + 1;\n";
+      o << "  const u64 base = (u64)blockIdx.x * " << tiles_k * cta_threads << "ull + threadIdx.x;\n";
+      auto emit_ib = [&](std::ostringstream& out) {
+        out << "    const u64 i0 = base + (u64)k * " << cta_threads << "ull;\n    const u64 i = i0 > mask ? mask : i0;\n";
+        for (unsigned b = 0; b <= max_back; b++) out << "    const u32 ib" << b << " = (u32)((i - " << 4 * b << "ull) & mask) << 2;\n";
+      };
+      for (size_t p = 0; p < np; p++) {
+        o << "  __syncthreads();\n#pragma unroll 1\n  for (int k = 0; k < " << tiles_k << "; k++) {\n";
+        emit_ib(o);
+        o << "    const PR" << p << " r = part" << p << "(" << ib_args;
+        for (unsigned u : part_ins[p]) o << ", " << slot(u);
+        o << ");\n";
+        for (size_t j = 0; j < part_outs[p].size(); j++) o << "    " << slot(part_outs[p][j]) << " = r.v[" << j << "];\n";
+        o << "  }\n";
+      }
+      o << "#pragma unroll 1\n  for (int k = 0; k < " << tiles_k << "; k++) {\n";
+      o << "    const u64 i = base + (u64)k * " << cta_threads << "ull;\n    if (i > mask) continue;\n";
+      o << "    const u32 iz = (i & 2) ? ((i & 1) ? iz3 : iz2) : ((i & 1) ? iz1 : iz0);\n";
+      for (int j = 0; j < 4; j++) {
+        std::string v = "0u";
+        if (result.ext || j == 0) v = result.c[j].tid >= 0 ? slot((unsigned)result.c[j].tid) : result.c[j].str();
+        o << "    check[" << j << " * domain + i] = fmul(" << v << ", iz);\n";
+      }
+      o << "  }\n}\n\n";
+    } else if (points_k == 1) {
       // same register cap as the 128-thread kernel (56): min_blocks CTAs of 128 threads == min_blocks * 128 / T CTAs of T threads
       const int mb = std::max(1, min_blocks * 128 / cta_threads);
       o << "extern \"C\" __global__ void __launch_bounds__(" << cta_threads << ", " << mb << ") b2z_eval_check(" << kernel_head_params << ") {\n";
@@ -923,6 +985,8 @@ b2z_err circuit_compile(b2z_ctx* ctx, b2z_circuit* c) {
   }
   B2Z_CUDA(cudaLibraryGetKernel(&c->k_eval_check, c->library, "b2z_eval_check"));
   B2Z_CUDA(cudaLibraryGetKernel(&c->k_witgen, c->library, "b2z_witgen"));
+  if (c->eval_smem_bytes > 48 * 1024)
+    B2Z_CUDA(cudaKernelSetAttributeForDevice(c->k_eval_check, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->eval_smem_bytes, ctx->device));
   if (c->parts_mode) {
     size_t bytes = 0;
     B2Z_CUDA(cudaLibraryGetGlobal(&c->ccp_dev, &bytes, c->library, "ccp"));

@@ -31,6 +31,8 @@ struct b2z_circuit {
   cudaKernel_t k_eval_check = nullptr, k_witgen = nullptr;
   bool parts_mode = false;                    // eval_check split into __noinline__ parts; tables in module constants
   unsigned eval_threads = 128;                // CTA size of the generated eval_check (B2Z_EVALCHECK_THREADS)
+  unsigned eval_tiles = 1;                    // tiles of eval_threads points per CTA (B2Z_EVALCHECK_TILES); state in shared memory
+  size_t eval_smem_bytes = 0;
   unsigned points_per_thread = 1;             // coset points per thread of the generated eval_check (parts mode, B2Z_EVALCHECK_POINTS)
   void *ccp_dev = nullptr, *ckc_dev = nullptr;  // device addresses of the module's __constant__ tables (parts mode)
   void *wcp_dev = nullptr, *wglobals_dev = nullptr;  // witgen: trace column pointers and the globals pointer (parts mode)

@@ -679,7 +679,8 @@ static void plan_chunks(const b2z_circuit* c, unsigned po2, size_t zk_rows, uint
                         const std::function<cudaEvent_t()>& next_event) {
   const size_t n = (size_t)1 << po2;
   const size_t wa = c->group_size[0], wc = c->group_size[1], wd = c->group_size[2];
-  ready.chunk_cols = 32;
+  // >= 256 MB of LDE per data chunk keeps the per-chunk launches (iNTT, LDE, persistent leaf-hash kernel) efficient
+  ready.chunk_cols = po2 >= 21 ? 32 : 64;
   ready.code_chunk_cols = 4;
   const size_t nchunks = (wd + ready.chunk_cols - 1) / ready.chunk_cols, ncode = (wc + ready.code_chunk_cols - 1) / ready.code_chunk_cols;
   for (size_t k = 0; k < ncode; k++) {
