@@ -482,6 +482,359 @@ static Val pw_val(uint32_t e, const std::string& kc_name = "kc") {
   return r;
 }
 
+
+// ---------------- staged eval_check: the tile's columns live in shared memory ----------------
+// The per-use tap loads of the straight-line program are its largest cost at rv32im scale: 18.6 k loads per point, 3 address
+// instructions each, 74 KB per point through L1 / L2 (ncu: 16.5 GB of DRAM reads for a 1 GB working set at po2 18).  Here a CTA
+// owns a tile of T = 128 consecutive coset points and first stages EVERY column of the three LDE matrices for that tile (plus a
+// halo of 4 * max_back rows for the columns that are tapped at earlier rows) into shared memory -- 144 KB for W = 256; every tap
+// of every point is then ONE `ld.shared` with a compile-time offset.  To fill the SM with one such tile resident, the constraint
+// program is split: the longest AndEqz / AndCond chain (a SUM of terms: tot(chain) = sum_k alpha^e_k * cond_k * value_k) is cut into
+// G contiguous ranges, thread group g (T threads) evaluates range g for all T points, the partial sums meet in shared memory and
+// group 0 runs the few steps after the chain.  Field arithmetic is exact, so the regrouped sum is bit-identical.
+struct DemandEmitter : Emitter {
+  std::vector<size_t> fp_def, mix_def;     // variable -> defining step
+  std::vector<char> have;
+  std::vector<uint32_t> tap_byte_off;      // per tap: byte offset of (this thread's row, this column, this back) from the thread's base
+  std::vector<size_t>* cut_points = nullptr;
+  struct MixAcc {
+    Val tot;
+    std::vector<std::pair<uint32_t, Opd>> pend;
+  };
+  std::map<size_t, MixAcc> mix_memo;
+  Val need(size_t v) {
+    if (!have[v]) {
+      const b2z_circuit::Step& s = c->steps[fp_def[v]];
+      Val r;
+      switch (s.op) {
+        case OP_CONST: r = base(konst(fp_from_u32(s.a))); break;
+        case OP_CONST_EXT:
+          r.ext = true;
+          r.c[0] = konst(fp_from_u32(s.a));
+          r.c[1] = konst(fp_from_u32(s.b));
+          r.c[2] = konst(fp_from_u32(s.c));
+          r.c[3] = konst(fp_from_u32(s.d));
+          break;
+        case OP_GET:
+          r.leaf_load = true;
+          r.load_expr = "lds(tp + " + std::to_string(tap_byte_off[s.a]) + "u)";
+          break;
+        case OP_GET_GLOBAL: r = base(named(kc_name + (s.a == 0 ? ".g[" : ".m[") + std::to_string(s.b) + "]")); break;
+        case OP_ADD: { Val x = need(s.a), y = need(s.b); r = v_add(x, y, false); } break;
+        case OP_SUB: { Val x = need(s.a), y = need(s.b); r = v_add(x, y, true); } break;
+        case OP_MUL: { Val x = need(s.a), y = need(s.b); r = v_mul(x, y); } break;
+        default: break;
+      }
+      vals[v] = r;
+      have[v] = 1;
+    }
+    return use(v);
+  }
+  void flush(MixAcc& m) {
+    if (m.pend.empty()) return;
+    for (int k = 0; k < 4; k++) {
+      std::string expr;
+      std::vector<Opd> ops;
+      size_t nterm = 0;
+      for (auto& pr : m.pend) {
+        if (pr.first == 0) continue;
+        expr += (nterm ? ", " : "") + kc_name + ".pw[" + std::to_string(4 * pr.first + k) + "], " + pr.second.str();
+        ops.push_back(pr.second);
+        nterm++;
+      }
+      if (nterm == 1) m.tot.c[k] = s_add(m.tot.c[k], emit_n("fmul(" + expr + ")", ops));
+      else if (nterm >= 2) m.tot.c[k] = s_add(m.tot.c[k], emit_n("dot" + std::to_string(nterm) + "(" + expr + ")", ops));
+    }
+    for (auto& pr : m.pend)
+      if (pr.first == 0) m.tot.c[0] = s_add(m.tot.c[0], pr.second);
+    m.pend.clear();
+  }
+  // total of mix variable m (iterative along its chain, recursive only into AndCond's inner chains)
+  MixAcc need_mix(size_t m) {
+    std::vector<size_t> path;
+    size_t cur = m;
+    while (!mix_memo.count(cur)) {
+      const b2z_circuit::Step& s = c->steps[mix_def[cur]];
+      if (s.op == OP_TRUE) {
+        MixAcc z;
+        z.tot.ext = true;
+        mix_memo[cur] = z;
+        break;
+      }
+      path.push_back(cur);
+      cur = s.a;
+    }
+    for (auto it = path.rbegin(); it != path.rend(); ++it) {
+      const b2z_circuit::Step& s = c->steps[mix_def[*it]];
+      MixAcc n = mix_memo[s.a];
+      if (s.op == OP_AND_EQZ) {
+        Val v = need(s.b);
+        if (!v.ext && !v.c[0].is_const) {
+          n.pend.push_back({c->mix_exp[s.a], v.c[0]});
+          if (n.pend.size() == 4) flush(n);
+        } else {
+          flush(n);
+          n.tot = v_add(n.tot, v_mul(pw_val(c->mix_exp[s.a], kc_name), v), false);
+        }
+      } else {  // OP_AND_COND
+        MixAcc in = need_mix(s.c);
+        flush(n);
+        flush(in);
+        Val cond = need(s.b);
+        Val inner = v_mul(in.tot, cond);
+        n.tot = v_add(n.tot, v_mul(inner, pw_val(c->mix_exp[s.a], kc_name)), false);
+      }
+      mix_memo[*it] = n;
+      if (cut_points) cut_points->push_back(stmts->size());
+    }
+    return mix_memo[m];
+  }
+};
+
+// cut a statement list into __noinline__ parts (same rule as the unstaged emitter); returns the calling sequence
+static std::string emit_staged_parts(std::ostringstream& o, const std::string& prefix, const std::vector<Emitter::Stmt>& stmts,
+                                     const std::vector<size_t>& cut_points, size_t parts_m, const std::vector<Opd>& live_out,
+                                     const std::string& extra_params, const std::string& extra_args) {
+  std::vector<size_t> bounds{0};
+  for (size_t cp_i : cut_points)
+    if (cp_i >= bounds.back() + parts_m && cp_i <= stmts.size()) bounds.push_back(cp_i);
+  if (bounds.back() != stmts.size()) bounds.push_back(stmts.size());
+  std::map<unsigned, size_t> def_part, last_use_part;
+  for (size_t p = 0; p + 1 < bounds.size(); p++)
+    for (size_t k = bounds[p]; k < bounds[p + 1]; k++) {
+      def_part[stmts[k].id] = p;
+      for (unsigned u : stmts[k].uses) last_use_part[u] = p;
+    }
+  const size_t FINAL = bounds.size();
+  for (const auto& x : live_out)
+    if (x.tid >= 0) last_use_part[(unsigned)x.tid] = FINAL;
+  std::ostringstream body;
+  for (size_t p = 0; p + 1 < bounds.size(); p++) {
+    std::vector<unsigned> ins, outs;
+    std::map<unsigned, bool> seen;
+    for (size_t k = bounds[p]; k < bounds[p + 1]; k++) {
+      for (unsigned u : stmts[k].uses)
+        if (def_part[u] < p && !seen[u]) {
+          seen[u] = true;
+          ins.push_back(u);
+        }
+      if (last_use_part.count(stmts[k].id) && last_use_part[stmts[k].id] > p) outs.push_back(stmts[k].id);
+    }
+    o << "struct " << prefix << "R" << p << " { u32 v[" << (outs.empty() ? 1 : outs.size()) << "]; };\n";
+    o << "static __device__ __noinline__ " << prefix << "R" << p << " " << prefix << "p" << p << "(" << extra_params;
+    for (unsigned u : ins) o << ", u32 t" << u;
+    o << ") {\n";
+    for (size_t k = bounds[p]; k < bounds[p + 1]; k++) o << "  const u32 t" << stmts[k].id << " = " << stmts[k].expr << ";\n";
+    o << "  " << prefix << "R" << p << " r;\n";
+    if (outs.empty()) o << "  r.v[0] = 0u;\n";
+    for (size_t j = 0; j < outs.size(); j++) o << "  r.v[" << j << "] = t" << outs[j] << ";\n";
+    o << "  return r;\n}\n";
+    body << "    const " << prefix << "R" << p << " " << prefix << "r" << p << " = " << prefix << "p" << p << "(" << extra_args;
+    for (unsigned u : ins) body << ", t" << u;
+    body << ");\n";
+    for (size_t j = 0; j < outs.size(); j++) body << "    const u32 t" << outs[j] << " = " << prefix << "r" << p << ".v[" << j << "];\n";
+  }
+  return body.str();
+}
+
+static bool codegen_eval_staged(b2z_circuit* c, std::ostringstream& o, int parts_m) {
+  constexpr unsigned T = 128;
+  int G = 8;
+  if (const char* e = getenv("B2Z_EVALCHECK_GROUPS")) G = atoi(e);
+  if (G < 1 || G > 8) G = 8;
+  const size_t ws[3] = {c->group_size[0] ? c->group_size[0] : 1, c->group_size[1] ? c->group_size[1] : 1, c->group_size[2] ? c->group_size[2] : 1};
+  const size_t flat0[3] = {0, ws[0], ws[0] + ws[1]};
+  const size_t ncol = ws[0] + ws[1] + ws[2];
+  // staging layout: column (g, col) keeps rows [i0 - halo, i0 + T), halo = 4 * deepest back of the column
+  std::vector<uint32_t> halo(ncol, 0), off(ncol, 0);
+  for (size_t t = 0; t < c->n_taps; t++) {
+    size_t f = flat0[c->tap_group[t]] + c->tap_offset[t];
+    halo[f] = std::max(halo[f], 4 * c->tap_back[t]);
+  }
+  size_t words = 0;
+  for (size_t f = 0; f < ncol; f++) {
+    off[f] = (uint32_t)words;
+    words += T + halo[f];
+  }
+  // variable -> defining step; the main chain = the longest AndEqz/AndCond chain
+  DemandEmitter proto{};
+  std::vector<size_t> fp_def, mix_def;
+  for (size_t i = 0; i < c->steps.size(); i++) {
+    uint32_t op = c->steps[i].op;
+    if (op == OP_TRUE || op == OP_AND_EQZ || op == OP_AND_COND) mix_def.push_back(i);
+    else fp_def.push_back(i);
+  }
+  const size_t nm = mix_def.size();
+  // The chain to split: start at `ret`; while ONE AndCond link of the current chain owns most of the constraints below it
+  // (weight = number of AndEqz / AndCond steps, nested chains included), descend into that link's inner chain.
+  std::vector<size_t> weight(nm, 0);
+  for (size_t m = 0; m < nm; m++) {
+    const auto& st = c->steps[mix_def[m]];
+    if (st.op != OP_TRUE) weight[m] = weight[st.a] + 1 + (st.op == OP_AND_COND ? weight[st.c] : 0);
+  }
+  size_t X = c->ret;
+  for (;;) {
+    size_t heavy = nm, heavy_w = 0;
+    for (size_t m = X; c->steps[mix_def[m]].op != OP_TRUE; m = c->steps[mix_def[m]].a) {
+      const auto& st = c->steps[mix_def[m]];
+      if (st.op == OP_AND_COND && weight[st.c] + 1 > heavy_w) {
+        heavy_w = weight[st.c] + 1;
+        heavy = m;
+      }
+    }
+    if (heavy == nm || 10 * heavy_w < 6 * weight[X]) break;
+    X = c->steps[mix_def[heavy]].c;
+  }
+  std::vector<size_t> chain;  // variables of the main chain, in order (without its True)
+  for (size_t m = X; c->steps[mix_def[m]].op != OP_TRUE; m = c->steps[mix_def[m]].a) chain.push_back(m);
+  std::reverse(chain.begin(), chain.end());
+  const size_t chain_true = chain.empty() ? X : c->steps[mix_def[chain.front()]].a;
+  std::vector<char> on_chain(nm, 0);
+  for (size_t m : chain) on_chain[m] = 1;
+  // only X may be referenced from outside the chain's own links (otherwise the split would need intermediate totals)
+  for (size_t m = 0; m < nm; m++) {
+    const auto& s = c->steps[mix_def[m]];
+    if (s.op == OP_TRUE) continue;
+    const bool next_link = on_chain[m];
+    if (!next_link && s.a != X && (on_chain[s.a] || (s.a == chain_true && !chain.empty() && false))) return false;
+    if (s.op == OP_AND_COND && on_chain[s.c] && s.c != X) return false;
+    if (next_link && s.op == OP_AND_COND && on_chain[s.c]) return false;
+  }
+  if ((int)chain.size() < 2 * G) G = 1;
+  const size_t smem_bytes = 4 * (words + 4 * (size_t)G * T);
+  if (smem_bytes > 220 * 1024) return false;  // wider circuits: fall back to per-use global loads
+  // tap -> byte offset from the thread's base (shared address of word `t` of the tile area)
+  std::vector<uint32_t> tap_byte_off(c->n_taps);
+  for (size_t t = 0; t < c->n_taps; t++) {
+    size_t f = flat0[c->tap_group[t]] + c->tap_offset[t];
+    tap_byte_off[t] = 4 * (off[f] + halo[f] - 4 * c->tap_back[t]);
+  }
+  auto make = [&](std::vector<Emitter::Stmt>& st, std::vector<size_t>& cuts) {
+    DemandEmitter em{};
+    em.c = c;
+    em.trace_domain = false;
+    em.o = &o;
+    em.stmts = &st;
+    em.kc_name = "ckc";
+    em.fp_def = fp_def;
+    em.mix_def = mix_def;
+    em.have.assign(fp_def.size(), 0);
+    em.vals.assign(fp_def.size(), Val());
+    em.tap_byte_off = tap_byte_off;
+    em.cut_points = &cuts;
+    return em;
+  };
+  // group ranges: equal numbers of generated statements (measured by a dry run over the whole chain)
+  std::vector<size_t> rng(G + 1, chain.size());
+  rng[0] = 0;
+  if (G > 1) {
+    std::vector<size_t> cum(chain.size(), 0);
+    {
+      std::vector<Emitter::Stmt> st;
+      std::vector<size_t> cuts;
+      DemandEmitter em = make(st, cuts);
+      DemandEmitter::MixAcc zero;
+      zero.tot.ext = true;
+      em.mix_memo[chain_true] = zero;
+      for (size_t k = 0; k < chain.size(); k++) {
+        em.need_mix(chain[k]);
+        cum[k] = st.size();
+      }
+    }
+    for (int g = 1; g < G; g++) {
+      const size_t target = cum.back() * g / G;
+      size_t k = rng[g - 1];
+      while (k < chain.size() && cum[k] < target) k++;
+      rng[g] = std::max(k, rng[g - 1]);
+    }
+  }
+  o << "__constant__ ColPtrs ccp;\n__constant__ Consts ckc;\n";
+  o << "__device__ __forceinline__ u32 lds(u32 a) { u32 v; asm volatile(\"ld.shared.u32 %0, [%1];\" : \"=r\"(v) : \"r\"(a)); return v; }\n";
+  o << "__constant__ u32 stg_off[" << ncol << "] = {";
+  for (size_t f = 0; f < ncol; f++) o << (f ? ", " : "") << off[f];
+  o << "};\n__constant__ u32 stg_halo[" << ncol << "] = {";
+  for (size_t f = 0; f < ncol; f++) o << (f ? ", " : "") << halo[f];
+  o << "};\n";
+  o << "// staging: warp w copies columns w, w + nwarps, ...: rows [i0 - halo, i0 + " << T << ") of the column, indices wrapped to the domain\n";
+  o << "__device__ __forceinline__ void stage_tile(u32* st, u64 i0, u64 mask) {\n"
+       "  const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;\n"
+       "  const u32* const* cols = reinterpret_cast<const u32* const*>(&ccp);\n"
+       "  for (unsigned col = warp; col < "
+    << ncol << "u; col += nw) {\n"
+       "    const u32* src = cols[col];\n    const unsigned h = stg_halo[col], n = "
+    << T << "u + h;\n    u32* dst = st + stg_off[col];\n"
+       "    for (unsigned r = lane; r < n; r += 32) dst[r] = __ldg(src + ((i0 - h + r) & mask));\n  }\n}\n";
+  // groups
+  std::vector<std::string> bodies(G);
+  std::vector<Val> partial(G);
+  for (int g = 0; g < G; g++) {
+    std::vector<Emitter::Stmt> st;
+    std::vector<size_t> cuts;
+    DemandEmitter em = make(st, cuts);
+    DemandEmitter::MixAcc zero;
+    zero.tot.ext = true;
+    Val tot = zero.tot;
+    if (rng[g + 1] > rng[g]) {
+      em.mix_memo[rng[g] == 0 ? chain_true : chain[rng[g] - 1]] = zero;
+      DemandEmitter::MixAcc r = em.need_mix(chain[rng[g + 1] - 1]);
+      em.flush(r);
+      tot = r.tot;
+    }
+    partial[g] = tot;
+    std::vector<Opd> live{tot.c[0], tot.c[1], tot.c[2], tot.c[3]};
+    bodies[g] = emit_staged_parts(o, "g" + std::to_string(g), st, cuts, (size_t)parts_m, live, "u32 tp", "tp");
+  }
+  // epilogue: the steps after the main chain, fed with the summed partial totals
+  std::string epi_body;
+  Val result;
+  {
+    std::vector<Emitter::Stmt> st;
+    std::vector<size_t> cuts;
+    DemandEmitter em = make(st, cuts);
+    em.tmp = 1u << 30;  // temporaries of the epilogue must not collide with s0..s3 / the groups' names
+    DemandEmitter::MixAcc xs;
+    xs.tot.ext = true;
+    for (int k = 0; k < 4; k++) xs.tot.c[k] = Emitter::named("s" + std::to_string(k));
+    if (!chain.empty()) em.mix_memo[X] = xs;
+    DemandEmitter::MixAcc r = em.need_mix(c->ret);
+    em.flush(r);
+    result = r.tot;
+    std::vector<Opd> live{result.c[0], result.c[1], result.c[2], result.c[3]};
+    epi_body = emit_staged_parts(o, "e", st, cuts, (size_t)parts_m, live, "u32 tp, u32 s0, u32 s1, u32 s2, u32 s3", "tp, s0, s1, s2, s3");
+  }
+  o << "extern \"C\" __global__ void __launch_bounds__(" << G * T << ", 1) b2z_eval_check(u32* __restrict__ check, u32 iz0, u32 iz1, u32 iz2, u32 iz3, u64 mask) {\n";
+  o << "  extern __shared__ u32 st[];\n  const u64 domain = mask + 1;\n";
+  o << "  const unsigned t = threadIdx.x & " << (T - 1) << "u, grp = threadIdx.x >> 7;\n";
+  o << "  const u64 i0 = (u64)blockIdx.x * " << T << "ull;\n  stage_tile(st, i0, mask);\n  __syncthreads();\n";
+  o << "  const u32 tp = (u32)__cvta_generic_to_shared(st) + 4u * t;\n  u32 p0 = 0u, p1 = 0u, p2 = 0u, p3 = 0u;\n";
+  for (int g = 0; g < G; g++) {
+    o << (g ? "  else if" : "  if") << " (grp == " << g << "u) {\n" << bodies[g];
+    for (int k = 0; k < 4; k++) o << "    p" << k << " = " << partial[g].c[k].str() << ";\n";
+    o << "  }\n";
+  }
+  o << "  u32* ps = st + " << words << "u;  // partial totals [4][" << G << "][" << T << "]\n";
+  for (int k = 0; k < 4; k++) o << "  ps[(" << k << "u * " << G << "u + grp) * " << T << "u + t] = p" << k << ";\n";
+  o << "  __syncthreads();\n  if (grp != 0u) return;\n";
+  for (int k = 0; k < 4; k++) {
+    o << "  u32 s" << k << " = ps[" << k * G * T << "u + t];\n";
+    for (int g = 1; g < G; g++) o << "  s" << k << " = fadd(s" << k << ", ps[" << (k * G + g) * T << "u + t]);\n";
+  }
+  o << "  {\n" << epi_body << "    const u64 i = i0 + t;\n    if (i > mask) return;\n";
+  o << "    const u32 iz = (i & 2) ? ((i & 1) ? iz3 : iz2) : ((i & 1) ? iz1 : iz0);\n";
+  for (int k = 0; k < 4; k++) {
+    std::string v = (result.ext || k == 0) ? result.c[k].str() : std::string("0u");
+    o << "    check[" << k << " * domain + i] = fmul(" << v << ", iz);\n";
+  }
+  o << "  }\n}\n\n";
+  c->parts_mode = true;
+  c->eval_threads = (unsigned)(G * T);
+  c->eval_tiles = 1;
+  c->points_per_thread = 1;
+  c->eval_points_per_cta = T;
+  c->eval_smem_bytes = smem_bytes;
+  return true;
+}
+
 void circuit_codegen(b2z_circuit* c) {
   std::ostringstream o;
   o << PRELUDE;
@@ -519,6 +872,20 @@ void circuit_codegen(b2z_circuit* c) {
   if (points_k < 1 || points_k > 8 || parts_m <= 0) points_k = 1;
   c->points_per_thread = (unsigned)points_k;
   const std::string cpn = parts_m > 0 ? "ccp" : "cp", kcn = parts_m > 0 ? "ckc" : "kc";
+  std::string ib_args, ib_params;
+  for (unsigned b = 0; b <= max_back; b++) {
+    ib_args += (b ? ", ib" : "ib") + std::to_string(b);
+    ib_params += (b ? ", u32 ib" : "u32 ib") + std::to_string(b);
+  }
+  c->eval_points_per_cta = 0;
+  // B2Z_EVALCHECK_STAGED=1 selects the shared-memory-staged form (codegen_eval_staged).  Measured on B200 (rv32im-scale program,
+  // po2 20): per-use global loads 35.7 ms, staged G = 8 / 6 / 4 groups 41.9 / 41.4 / 44.2 ms; planning circuit 1.84 vs 3.95 ms.
+  // ncu of the staged kernel (profiles/r2_prof_evalcheck_staged_ncu.txt): DRAM reads 1.08 GB instead of 16.5 GB, 24 % fewer
+  // instructions, L2 throughput < 1 % -- but issue 35 % with `no_instruction` at 17 stalled warps per issue: eight different
+  // instruction streams per SM, each shared by only four warps, are bound by instruction-FETCH latency.  Off by default.
+  bool staged = parts_m > 0 && points_k == 1 && getenv("B2Z_EVALCHECK_STAGED") && getenv("B2Z_EVALCHECK_STAGED")[0] == '1';
+  if (staged) staged = codegen_eval_staged(c, o, parts_m);
+  if (!staged) {
   std::ostringstream body;  // straight-line mode: kernel body text
   std::vector<Emitter::Stmt> stmts;
   std::vector<size_t> cut_points;  // statement counts at which a cut is allowed
@@ -629,11 +996,6 @@ void circuit_codegen(b2z_circuit* c) {
     }
     out << "}\n\n";
   };
-  std::string ib_args, ib_params;
-  for (unsigned b = 0; b <= max_back; b++) {
-    ib_args += (b ? ", ib" : "ib") + std::to_string(b);
-    ib_params += (b ? ", u32 ib" : "u32 ib") + std::to_string(b);
-  }
   if (parts_m <= 0) {
     o << "extern \"C\" __global__ void __launch_bounds__(128, " << min_blocks << ") b2z_eval_check(" << kernel_head_params << ") {\n";
     o << "  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;\n  if (i > mask) return;\n  const u64 domain = mask + 1;\n";
@@ -816,6 +1178,7 @@ void circuit_codegen(b2z_circuit* c) {
       o << "}\n\n";
     }
   }
+  }  // !staged
   // ---- witgen: one thread per active trace row; taps read the trace domain (stride 1) ----
   if (parts_m <= 0) {
     o << "extern \"C\" __global__ void __launch_bounds__(256) b2z_witgen(const __grid_constant__ ColPtrs cp, "
