@@ -203,6 +203,11 @@ b2z_err b2z_session_set_control_root(b2z_session* s, unsigned po2, const uint32_
  * session), SegmentReceipts assembled in index order.  Free the result with b2z_receipt_free. */
 b2z_err b2z_prove_session(b2z_session* s, const b2z_segment_input* segments, size_t n_segments, const uint8_t* journal,
                           size_t journal_len, b2z_receipt** out);
+/* Seal cache / resume: with a directory set, proved seals are stored there keyed by (circuit, po2, index, header digest) and
+ * a later session loads them instead of proving again (re-verified first when a control root is registered).  NULL / ""
+ * switches it off.  The reference's analogue is its input cache, /root/reference crates/host/src/bin/cli.rs:113-145. */
+b2z_err b2z_session_set_seal_cache(b2z_session* s, const char* dir);
+size_t b2z_session_last_cache_hits(const b2z_session* s);
 uint64_t b2z_session_launch_count(const b2z_session* s);
 double b2z_session_last_wall_ms(const b2z_session* s);
 size_t b2z_session_last_retries(const b2z_session* s);

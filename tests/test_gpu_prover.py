@@ -368,3 +368,36 @@ def test_mux_circuit_seal_parity(hal, oracle, mk, po2):
     with pytest.raises(H.B2ZError, match="does not satisfy"):
         hal.prove_segment(c, po2, code, bad, glob, noise, zk)
     c.close()
+
+
+def test_session_seal_cache_resumes(hal, oracle, tmp_path):
+    """Seal cache / resume: the second run of a session finds every seal on disk (no kernel is launched), a
+    corrupted cache file is detected by the verifier and only that segment is proved again."""
+    sc = S.circuit_planning()
+    po2, zk, seed0 = 11, 512, 0xB2000000 + 3000
+    oc = oracle.Circuit(sc.blob)
+    sess = H.Session(0, sc.blob, in_flight=2)
+    wit, want = [], []
+    for i in range(4):
+        code, data, glob, noise = oc.witgen(po2, seed0 + i, zk)
+        want.append(oc.prove(po2, code, data, glob, noise, zk))
+        wit.append(dict(po2=po2, code=code, data=data, globals=glob, accum_noise=noise, zk_rows=zk, on_device=False))
+    sess.set_control_root(po2, oc.control_roots[po2])
+    sess.set_seal_cache(str(tmp_path))
+    r1 = sess.prove(wit)
+    assert sess.last_cache_hits() == 0 and len(list(tmp_path.glob("seal_*.bin"))) == 4
+    launches = sess.launch_count()
+    r2 = sess.prove(wit)
+    assert sess.last_cache_hits() == 4 and sess.launch_count() == launches
+    assert all(np.array_equal(r2.seal(i), want[i]) and np.array_equal(r1.seal(i), want[i]) for i in range(4))
+    victim = sorted(tmp_path.glob("seal_*_2_*.bin"))[0]  # the file of segment index 2
+    raw = bytearray(victim.read_bytes())
+    raw[len(raw) // 2] ^= 1
+    victim.write_bytes(bytes(raw))
+    r3 = sess.prove(wit)
+    assert sess.last_cache_hits() == 3 and sess.launch_count() > launches
+    assert all(np.array_equal(r3.seal(i), want[i]) for i in range(4))
+    sess.set_seal_cache(None)
+    sess.prove(wit[:1])
+    assert sess.last_cache_hits() == 0
+    sess.close()

@@ -30,13 +30,12 @@ def _worker(rank, world, port, n_segments, seal_words, q):
     local = {i: (np.arange(seal_words, dtype=np.uint32) * np.uint32(table[i][1])) for i in mine}
     seals = shard.gather_seals(local, n_segments, seal_words, dev)
     # the block job's gather (bench.py): equal shares, rank r holds segments r, r + world, ... in that order
-    per_rank = (n_segments + world - 1) // world
-    mine2 = [i for i in range(world * per_rank) if i % world == rank]
-    seals2 = shard.all_gather_seals([np.arange(seal_words, dtype=np.uint32) * np.uint32(7 + i) for i in mine2], per_rank, seal_words, dev)
+    mine2 = [i for i in range(n_segments) if i % world == rank]  # 5 segments over 2 ranks: ragged shares
+    seals2 = shard.all_gather_seals([np.arange(seal_words, dtype=np.uint32) * np.uint32(7 + i) for i in mine2], n_segments, seal_words, dev)
     if rank == 0:
         ok = all(np.array_equal(seals[i], np.arange(seal_words, dtype=np.uint32) * np.uint32(1000 + i)) for i in range(n_segments))
-        ok = ok and len(seals2) == world * per_rank and all(
-            np.array_equal(seals2[i], np.arange(seal_words, dtype=np.uint32) * np.uint32(7 + i)) for i in range(world * per_rank))
+        ok = ok and len(seals2) == n_segments and all(
+            np.array_equal(seals2[i], np.arange(seal_words, dtype=np.uint32) * np.uint32(7 + i)) for i in range(n_segments))
         q.put((ok, [int(t[1]) for t in table]))
     else:
         assert seals2 is None

@@ -50,6 +50,23 @@ B2Z_HD uint32_t fp_mul(uint32_t a, uint32_t b) {
   return umin32(r, r + P);
 }
 B2Z_HD uint32_t fp_sqr(uint32_t a) { return fp_mul(a, a); }
+// a0*b0 + a1*b1 + a2*b2 + a3*b3 (Montgomery products) with ONE reduction: every product of canonical words is < P^2 and
+// 4 P^2 < 2^64, so the four terms accumulate in 64 bits (one IMAD.WIDE each); the high word (< 2^32 < 3 P) is brought below P
+// by two conditional subtractions and one Montgomery step finishes: 10 instructions instead of 4 products + 3 adds (26).
+B2Z_HD uint32_t fp_dot4(uint32_t a0, uint32_t b0, uint32_t a1, uint32_t b1, uint32_t a2, uint32_t b2, uint32_t a3, uint32_t b3) {
+  uint64_t x = (uint64_t)a0 * b0 + (uint64_t)a1 * b1 + (uint64_t)a2 * b2 + (uint64_t)a3 * b3;
+  uint32_t hi = (uint32_t)(x >> 32), lo = (uint32_t)x;
+  hi = umin32(hi, hi - P);
+  hi = umin32(hi, hi - P);
+  uint32_t m = lo * MONT_PINV;
+#if defined(__CUDA_ARCH__)
+  uint32_t u = __umulhi(m, P);
+#else
+  uint32_t u = (uint32_t)(((uint64_t)m * P) >> 32);
+#endif
+  uint32_t r = hi - u;
+  return umin32(r, r + P);
+}
 B2Z_HD uint32_t fp_from_u32(uint32_t x) { return fp_mul(x % P, MONT_R2); }
 B2Z_HD uint32_t fp_to_u32(uint32_t a) { return fp_mul(a, 1u); }
 B2Z_HD uint32_t fp_pow(uint32_t a, uint64_t n) {
@@ -87,15 +104,15 @@ B2Z_HD Fp4 fp4_sub_fp(const Fp4& a, uint32_t b) { return fp4_make(fp_sub(a.e[0],
 B2Z_HD Fp4 fp4_mul_fp(const Fp4& a, uint32_t b) {
   return fp4_make(fp_mul(a.e[0], b), fp_mul(a.e[1], b), fp_mul(a.e[2], b), fp_mul(a.e[3], b));
 }
+// (a0 + a1 x + a2 x^2 + a3 x^3)(b0 + ...) mod x^4 - 11: every output component is a sum of four products -> one fp_dot4 each
+// (3 products by beta + 4 single-reduction dot products instead of 19 products and 12 modular adds)
 B2Z_HD Fp4 fp4_mul(const Fp4& a, const Fp4& b) {
+  const uint32_t ba1 = fp_mul(MONT_BETA, a.e[1]), ba2 = fp_mul(MONT_BETA, a.e[2]), ba3 = fp_mul(MONT_BETA, a.e[3]);
   Fp4 r;
-  r.e[0] = fp_add(fp_mul(a.e[0], b.e[0]),
-                  fp_mul(MONT_BETA, fp_add(fp_add(fp_mul(a.e[1], b.e[3]), fp_mul(a.e[2], b.e[2])), fp_mul(a.e[3], b.e[1]))));
-  r.e[1] = fp_add(fp_add(fp_mul(a.e[0], b.e[1]), fp_mul(a.e[1], b.e[0])),
-                  fp_mul(MONT_BETA, fp_add(fp_mul(a.e[2], b.e[3]), fp_mul(a.e[3], b.e[2]))));
-  r.e[2] = fp_add(fp_add(fp_add(fp_mul(a.e[0], b.e[2]), fp_mul(a.e[1], b.e[1])), fp_mul(a.e[2], b.e[0])),
-                  fp_mul(MONT_BETA, fp_mul(a.e[3], b.e[3])));
-  r.e[3] = fp_add(fp_add(fp_mul(a.e[0], b.e[3]), fp_mul(a.e[1], b.e[2])), fp_add(fp_mul(a.e[2], b.e[1]), fp_mul(a.e[3], b.e[0])));
+  r.e[0] = fp_dot4(a.e[0], b.e[0], ba1, b.e[3], ba2, b.e[2], ba3, b.e[1]);
+  r.e[1] = fp_dot4(a.e[0], b.e[1], a.e[1], b.e[0], ba2, b.e[3], ba3, b.e[2]);
+  r.e[2] = fp_dot4(a.e[0], b.e[2], a.e[1], b.e[1], a.e[2], b.e[0], ba3, b.e[3]);
+  r.e[3] = fp_dot4(a.e[0], b.e[3], a.e[1], b.e[2], a.e[2], b.e[1], a.e[3], b.e[0]);
   return r;
 }
 B2Z_HD Fp4 fp4_pow(Fp4 a, uint64_t n) {

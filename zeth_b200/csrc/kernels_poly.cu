@@ -85,10 +85,10 @@ __global__ void __launch_bounds__(EA_THREADS) ea_dot_kernel(const uint32_t* __re
 #pragma unroll
       for (unsigned e = 0; e < EA_GROUP; e++) {
         Fp4 a = acc[e];
-        a.e[0] = fp_add(a.e[0], fp_add(fp_add(fp_mul(p0.x, cv[e].x), fp_mul(p1.x, cv[e].y)), fp_add(fp_mul(p2.x, cv[e].z), fp_mul(p3.x, cv[e].w))));
-        a.e[1] = fp_add(a.e[1], fp_add(fp_add(fp_mul(p0.y, cv[e].x), fp_mul(p1.y, cv[e].y)), fp_add(fp_mul(p2.y, cv[e].z), fp_mul(p3.y, cv[e].w))));
-        a.e[2] = fp_add(a.e[2], fp_add(fp_add(fp_mul(p0.z, cv[e].x), fp_mul(p1.z, cv[e].y)), fp_add(fp_mul(p2.z, cv[e].z), fp_mul(p3.z, cv[e].w))));
-        a.e[3] = fp_add(a.e[3], fp_add(fp_add(fp_mul(p0.w, cv[e].x), fp_mul(p1.w, cv[e].y)), fp_add(fp_mul(p2.w, cv[e].z), fp_mul(p3.w, cv[e].w))));
+        a.e[0] = fp_add(a.e[0], fp_dot4(p0.x, cv[e].x, p1.x, cv[e].y, p2.x, cv[e].z, p3.x, cv[e].w));
+        a.e[1] = fp_add(a.e[1], fp_dot4(p0.y, cv[e].x, p1.y, cv[e].y, p2.y, cv[e].z, p3.y, cv[e].w));
+        a.e[2] = fp_add(a.e[2], fp_dot4(p0.z, cv[e].x, p1.z, cv[e].y, p2.z, cv[e].z, p3.z, cv[e].w));
+        a.e[3] = fp_add(a.e[3], fp_dot4(p0.w, cv[e].x, p1.w, cv[e].y, p2.w, cv[e].z, p3.w, cv[e].w));
         acc[e] = a;
       }
     }

@@ -262,7 +262,8 @@ struct b2z_session {
   };
   std::vector<Worker> workers;
   double last_wall_ms = 0;
-  size_t last_retries = 0;
+  size_t last_retries = 0, last_cache_hits = 0;
+  std::string seal_cache_dir;  // optional on-disk seal cache (resume of a long session)
   std::vector<double> last_segment_ms;
 };
 
@@ -320,6 +321,45 @@ size_t b2z_session_last_segment_ms(const b2z_session* s, double* ms, size_t cap)
   return s->last_segment_ms.size();
 }
 
+// Seal cache (SURVEY.md 5 "checkpoint / resume"; the reference's analogue is its input cache, crates/host/src/bin/cli.rs:113-145):
+// with a directory set, every proved segment's seal is written to <dir>/seal_<circuit>_<po2>_<index>_<header digest>.bin and a
+// later session that meets the same (circuit, po2, index, header = globals || po2) loads it instead of proving -- a 500-segment
+// job that died at segment 400 resumes there.  The header digest ties the file to the segment's public state (pre / post
+// digests live in the globals); a cached seal is re-verified before it is trusted when a control root is registered.
+b2z_err b2z_session_set_seal_cache(b2z_session* s, const char* dir) {
+  B2Z_REQUIRE(s, "null session");
+  s->seal_cache_dir = dir ? dir : "";
+  return nullptr;
+}
+size_t b2z_session_last_cache_hits(const b2z_session* s) { return s ? s->last_cache_hits : 0; }
+
+static std::string seal_cache_path(const b2z_session* s, const b2z_circuit* c, const b2z_segment_input& g) {
+  uint32_t vp[8], hd[8];
+  verifier_parameters(c, vp);
+  std::vector<uint32_t> header(g.globals, g.globals + c->globals_size);
+  header.push_back(fp_from_u32(g.po2));
+  host_hash_elem_slice(header.data(), header.size(), hd);
+  char name[160];
+  snprintf(name, sizeof name, "/seal_%08x%08x_%u_%u_%08x%08x%08x%08x.bin", vp[0], vp[1], g.po2, g.index, hd[0], hd[1], hd[2], hd[3]);
+  return s->seal_cache_dir + name;
+}
+static bool seal_cache_load(const std::string& path, std::vector<uint32_t>& seal) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  bool ok = fread(seal.data(), 4, seal.size(), f) == seal.size() && fgetc(f) == EOF;
+  fclose(f);
+  return ok;
+}
+static void seal_cache_store(const std::string& path, const std::vector<uint32_t>& seal) {
+  std::string tmp = path + ".tmp." + std::to_string((unsigned long long)(uintptr_t)&seal);
+  FILE* f = fopen(tmp.c_str(), "wb");
+  if (!f) return;
+  bool ok = fwrite(seal.data(), 4, seal.size(), f) == seal.size();
+  ok = fclose(f) == 0 && ok;
+  if (ok) ok = rename(tmp.c_str(), path.c_str()) == 0;
+  if (!ok) remove(tmp.c_str());
+}
+
 b2z_err b2z_session_set_control_root(b2z_session* s, unsigned po2, const uint32_t* root8) {
   B2Z_REQUIRE(s && root8, "null argument");
   for (auto& w : s->workers) B2Z_TRY(b2z_circuit_set_control_root(w.circuit, po2, root8));
@@ -338,7 +378,17 @@ b2z_err b2z_prove_session(b2z_session* s, const b2z_segment_input* segs, size_t 
     seals[i].resize(circuit_seal_words(c0, segs[i].po2));
   }
   s->last_segment_ms.assign(n, 0.0);
-  std::atomic<size_t> next{0}, retries{0};
+  std::atomic<size_t> next{0}, retries{0}, cache_hits{0};
+  // seals already on disk are taken first (single-threaded, host only): the workers then see them as done
+  std::vector<char> done(n, 0);
+  if (!s->seal_cache_dir.empty())
+    for (size_t i = 0; i < n; i++) {
+      if (!seal_cache_load(seal_cache_path(s, c0, segs[i]), seals[i])) continue;
+      const bool bound = segs[i].po2 < 32 && c0->has_control_root[segs[i].po2];
+      if (bound && verify_segment(c0, seals[i].data(), seals[i].size()) != 0) continue;  // stale / corrupt file: prove again
+      done[i] = 1;
+      cache_hits.fetch_add(1);
+    }
   std::mutex err_mutex;
   std::string first_error;
   std::atomic<bool> failed{false};
@@ -348,12 +398,18 @@ b2z_err b2z_prove_session(b2z_session* s, const b2z_segment_input* segs, size_t 
     cudaSetDevice(s->device);
     // the worker claims its NEXT segment early and starts that witness's upload (pinned host sources) before it proves the
     // current one: PCIe runs decoupled from the commit phases, and two workers do not fall into upload-bound lockstep
+    auto claim = [&]() {  // next segment that still has to be proved
+      size_t i;
+      do i = next.fetch_add(1);
+      while (i < n && done[i]);
+      return i;
+    };
     auto begin = [&](size_t i, HostUpload** up) {
       *up = nullptr;
       if (i < n && !segs[i].on_device && !failed.load())
         host_upload_begin(w.ctx, w.circuit, segs[i].po2, segs[i].code, segs[i].data, segs[i].accum_noise, segs[i].zk_rows, up);  // NULL on pageable sources / errors
     };
-    size_t i_next = next.fetch_add(1);
+    size_t i_next = claim();
     HostUpload* up_next = nullptr;
     begin(i_next, &up_next);
     for (;;) {
@@ -363,7 +419,7 @@ b2z_err b2z_prove_session(b2z_session* s, const b2z_segment_input* segs, size_t 
         host_upload_discard(w.ctx, up);
         return;
       }
-      i_next = next.fetch_add(1);
+      i_next = claim();
       begin(i_next, &up_next);
       const b2z_segment_input& g = segs[i];
       b2z_err e = nullptr;
@@ -388,6 +444,7 @@ b2z_err b2z_prove_session(b2z_session* s, const b2z_segment_input* segs, size_t 
         }
       }
       s->last_segment_ms[i] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ts).count();
+      if (!e && !s->seal_cache_dir.empty()) seal_cache_store(seal_cache_path(s, w.circuit, g), seals[i]);
       if (e) {
         std::lock_guard<std::mutex> lock(err_mutex);
         if (first_error.empty()) first_error = "segment " + std::to_string(g.index) + ": " + e;
@@ -407,6 +464,7 @@ b2z_err b2z_prove_session(b2z_session* s, const b2z_segment_input* segs, size_t 
   }
   s->last_wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   s->last_retries = retries.load();
+  s->last_cache_hits = cache_hits.load();
   if (failed.load()) return set_error(first_error);
   std::vector<const uint32_t*> ptrs(n);
   std::vector<size_t> lens(n);

@@ -35,7 +35,7 @@ _ERR_FUNCS = [
     "b2z_eltwise_zeroize_elem", "b2z_gather_sample", "b2z_poly_divide", "b2z_circuit_load", "b2z_circuit_precompile",
     "b2z_circuit_free", "b2z_eval_check", "b2z_accumulate", "b2z_witgen", "b2z_prove_segment_device", "b2z_prove_segment",
     "b2z_scatter", "b2z_prefix_products", "b2z_compute_control_root", "b2z_circuit_set_control_root",
-    "b2z_session_create", "b2z_session_destroy", "b2z_session_set_control_root", "b2z_prove_session",
+    "b2z_session_create", "b2z_session_destroy", "b2z_session_set_control_root", "b2z_session_set_seal_cache", "b2z_prove_session",
     "b2z_receipt_assemble", "b2z_receipt_free", "b2z_receipt_serialize", "b2z_receipt_deserialize",
 ]
 
@@ -75,6 +75,8 @@ def load_library():
     L.b2z_session_last_retries.restype = C.c_size_t
     L.b2z_session_last_retries.argtypes = [C.c_void_p]
     L.b2z_session_last_segment_ms.restype = C.c_size_t
+    L.b2z_session_last_cache_hits.restype = C.c_size_t
+    L.b2z_session_last_cache_hits.argtypes = [C.c_void_p]
     L.b2z_bytes_free.restype = None
     L.b2z_bytes_free.argtypes = [C.c_void_p]
     _LIB = L
@@ -467,6 +469,13 @@ class Session:
         j = (C.c_uint8 * max(len(journal), 1)).from_buffer_copy(journal.ljust(1, b"\0"))
         _chk(self.L.b2z_prove_session(self.h, arr, C.c_size_t(len(segments)), j, C.c_size_t(len(journal)), C.byref(p)))
         return Receipt(p)
+
+    def set_seal_cache(self, directory: str | None):
+        """Seal cache / resume: proved seals are stored under `directory` and reused by later sessions."""
+        _chk(self.L.b2z_session_set_seal_cache(self.h, directory.encode() if directory else None))
+
+    def last_cache_hits(self) -> int:
+        return int(self.L.b2z_session_last_cache_hits(self.h))
 
     def launch_count(self) -> int:
         return int(self.L.b2z_session_launch_count(self.h))

@@ -62,14 +62,16 @@ def gather_seals(local: dict[int, np.ndarray], n_segments: int, seal_words: int,
 
 
 
-def all_gather_seals(local_seals: list, per_rank: int, seal_words: int, device: torch.device) -> list[np.ndarray] | None:
-    """The block job's seal gather: rank r holds the seals of segments r, r + world, r + 2 world, ... (`per_rank` of them, in that
-    order); ONE all_gather_into_tensor of exact seal words from a pinned staging buffer brings every seal to every rank, and
+def all_gather_seals(local_seals: list, n_total: int, seal_words: int, device: torch.device) -> list[np.ndarray] | None:
+    """The block job's seal gather: of `n_total` segments rank r holds the seals of segments r, r + world, r + 2 world, ... in that
+    order; ONE all_gather_into_tensor of exact seal words from a pinned staging buffer brings every seal to every rank, and
     rank 0 returns them in segment order (None on the other ranks).  Shorter shares are padded with zero rows."""
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
     if world == 1:
         return [np.asarray(s, dtype=np.uint32) for s in local_seals]
+    per_rank = (n_total + world - 1) // world
+    assert len(local_seals) == len(range(rank, n_total, world))
     stage = torch.zeros((per_rank, seal_words), dtype=torch.int32)
     if device.type == "cuda":
         stage = stage.pin_memory()
@@ -82,4 +84,4 @@ def all_gather_seals(local_seals: list, per_rank: int, seal_words: int, device: 
     if rank != 0:
         return None
     host = allg.cpu().numpy().view(np.uint32)
-    return [host[(i % world) * per_rank + i // world] for i in range(world * per_rank)]
+    return [host[(i % world) * per_rank + i // world] for i in range(n_total)]
