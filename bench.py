@@ -490,6 +490,10 @@ def run_block_workload(args):
     hal0, circuit = sess.hals[0], sess.circuit
     seal_words = circuit.seal_words(po2)
 
+    def gather(receipt, n_total):
+        """every rank's seals -> rank 0: one all_gather of exact seal words from a pinned staging buffer (zeth_b200/shard.py)"""
+        return shard.all_gather_seals([receipt.seal(i) for i in range(receipt.n_segments)], n_total, seal_words, dev)
+
     # segment table (index, seed, po2) decided by rank 0, NCCL broadcast; the job = W*S warm-up + K*S timed segments
     n_warm, n_timed = W * S, K * S
     table = np.array([[i, SEED0 + 1000 + i, po2] for i in range(n_warm + n_timed)], dtype=np.int64) if rank == 0 else None
@@ -528,15 +532,12 @@ def run_block_workload(args):
     wit = [gen(sg) for sg in timed_ids]
     for k, wt in enumerate(wit):
         wt["index"] = k
-    sess.set_control_root(po2, hal0.compute_control_root(po2, wit[0]["code"], wc))
+    if wit:  # (a rank may have no timed segment when K * S < world)
+        sess.set_control_root(po2, hal0.compute_control_root(po2, wit[0]["code"], wc))
     launches0 = sess.launch_count()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-
-    def gather(receipt, n_total):
-        """every rank's seals -> rank 0: one all_gather of exact seal words from a pinned staging buffer (zeth_b200/shard.py)"""
-        return shard.all_gather_seals([receipt.seal(i) for i in range(receipt.n_segments)], n_total, seal_words, dev)
 
     if world > 1:
         dist.barrier()
