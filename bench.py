@@ -526,6 +526,8 @@ def run_block_workload(args):
         del pad
     if n_warm:
         gather(wr, n_warm)
+    if world > 1:  # the retry protocol's all-reduce, first use
+        dist.all_reduce(torch.zeros(n_timed + world, dtype=torch.int32, device=dev), op=dist.ReduceOp.MAX)
     wr.close()
     code0 = wit[0]["_t"][0] if wit else None
     del wit
@@ -534,6 +536,19 @@ def run_block_workload(args):
         wt["index"] = k
     if wit:  # (a rank may have no timed segment when K * S < world)
         sess.set_control_root(po2, hal0.compute_control_root(po2, wit[0]["code"], wc))
+    receipts, share_s = [], [0.0]
+
+    def prove_share(indices):
+        """this rank's share of the timed job (resident witnesses); a share re-assigned from a failed rank is regenerated from
+        the broadcast segment table first"""
+        ta = time.perf_counter()
+        own = indices == shard.partition(n_timed, world, rank)
+        ws = wit if own else [dict(gen(n_warm + i), index=k) for k, i in enumerate(indices)]
+        r = sess.prove(ws, journal=b"")
+        receipts.append(r)
+        share_s[0] += time.perf_counter() - ta
+        return [r.seal(k) for k in range(r.n_segments)]
+
     launches0 = sess.launch_count()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -545,9 +560,10 @@ def run_block_workload(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()
-    receipt = sess.prove(wit, journal=b"")         # timed: this rank's share, `in_flight` segments at a time
-    t_prove = time.perf_counter()
-    seals = gather(receipt, n_timed)               # timed: NCCL gather of every seal to rank 0
+    # timed: this rank's share through b2z_prove_session (`in_flight` segments at a time), the failure-flag all-reduce of the
+    # cross-rank retry protocol, and the NCCL gather of every seal to rank 0 (zeth_b200/shard.py::prove_sharded)
+    seals, reassigned = shard.prove_sharded(n_timed, prove_share, seal_words, dev)
+    t_prove = t0 + share_s[0]
     e1.record()
     torch.cuda.synchronize()
     t1 = time.perf_counter()
@@ -563,6 +579,13 @@ def run_block_workload(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     max_ms, gather_ms = float(t[0].item()), float(t[1].item())
     value = n_timed * n / (max_ms * 1e-3)
+    # per-rank time inside b2z_prove_session (diagnostic: the spread is what the fastest rank waits for in the gather)
+    mine = torch.tensor([(t_prove - t0) * 1e3], dtype=torch.float64, device=dev)
+    rank_prove_ms = [float(mine.item())]
+    if world > 1:
+        allp = torch.empty(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allp, mine)
+        rank_prove_ms = [round(float(x), 1) for x in allp.cpu()]
 
     # receipt check on rank 0 (untimed): the first few segments of the assembled session through Receipt::verify
     verified = None
@@ -579,7 +602,8 @@ def run_block_workload(args):
         buf = (__import__("ctypes").c_double * 4096)()
         cnt = int(sess.L.b2z_session_last_segment_ms(sess.h, buf, 4096))
         per_seg_ms = float(np.median([buf[i] for i in range(min(cnt, 4096))])) if cnt else None
-    receipt.close()
+    for r in receipts:
+        r.close()
 
     # ---- e2e: the same session call with HOST (pinned) witnesses: H2D of every witness + proving + seal D2H + gather ----
     e2e_steps = max(1, min(K, 3))
@@ -653,7 +677,7 @@ def run_block_workload(args):
                        "segments_total": n_timed, "cycles_total": n_timed * n, "in_flight_per_gpu": sess.in_flight,
                        "parallelism": f"independent segments round-robin over {world} GPU(s); NCCL broadcast of the segment table, "
                                       f"all_gather of the seals (inside the timed region)",
-                       "seal_gather_ms": gather_ms, "segment_retries": retries, "receipt_verified_segments": verified,
+                       "seal_gather_ms": gather_ms, "rank_prove_ms": rank_prove_ms, "segment_retries": retries, "segments_reassigned_across_ranks": reassigned, "receipt_verified_segments": verified,
                        "median_segment_latency_ms": per_seg_ms, "phase_ms_per_segment": phase_ms,
                        "l2": "inputs >> L2 (0.87 GB of witness per segment), no flush needed",
                        "timing": "witnesses resident in HBM; barrier + synchronize, CUDA events around [prove_session + seal gather], "

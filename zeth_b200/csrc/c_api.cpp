@@ -70,6 +70,7 @@ b2z_err b2z_destroy(b2z_ctx* ctx) {
   }
   for (auto e : ctx->h2d_events) cudaEventDestroy(e);
   for (auto e : ctx->event_pool) cudaEventDestroy(e);
+  if (ctx->wait_event) cudaEventDestroy(ctx->wait_event);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
   if (ctx->aux_fork) cudaEventDestroy(ctx->aux_fork);

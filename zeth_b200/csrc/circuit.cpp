@@ -333,6 +333,10 @@ struct Emitter {
   };
   std::vector<Stmt>* stmts = nullptr;
   std::string cp_name = "cp", kc_name = "kc", glob_name = "globals";
+  // tiled mode (eval_check over the tiled LDE copy): a tap is `ldt(pt + constant)`; flat column index = tile_flat0[group] + column
+  bool tiled = false;
+  size_t tile_flat0[3] = {0, 0, 0};
+  unsigned tile_pitch_bytes = 0;
   Opd emit(const std::string& expr, const Opd* a = nullptr, const Opd* b = nullptr) {
     unsigned id = tmp++;
     std::string n = "t" + std::to_string(id);
@@ -451,6 +455,10 @@ struct Emitter {
         r.load_col = cp_name + ".g" + std::to_string(g) + "[" + std::to_string(col) + "]";
         r.load_off = "ib" + std::to_string(back);
         r.load_expr = "ldc(" + r.load_col + ", " + r.load_off + ")";
+        if (tiled) {
+          const long long off = (long long)(tile_flat0[g] + col) * tile_pitch_bytes - 16ll * back;
+          r.load_expr = "ldt(pt + (" + std::to_string(off) + "))";
+        }
       } break;
       case OP_GET_GLOBAL:
         if (trace_domain) {
@@ -878,6 +886,26 @@ void circuit_codegen(b2z_circuit* c) {
     ib_params += (b ? ", u32 ib" : "u32 ib") + std::to_string(b);
   }
   c->eval_points_per_cta = 0;
+  // B2Z_EVALCHECK_TILED (default 0; parts mode, one point per thread, no tile looping): tap loads go to a TILED copy of the three LDE
+  // matrices, [tile of 128 points][column][halo + 128 rows] with the halo = 4 * max_back rows that precede the tile (wrapped to
+  // the domain), built by one transpose kernel per eval_check.  Every tap of a thread is then its row pointer plus a COMPILE-TIME
+  // offset (column * pitch - 16 * back): ONE LDG with an immediate instead of IADD3 + IMAD.X + LDG -- a third of the program's
+  // instructions were tap-address arithmetic -- and the eight row-offset registers per thread disappear.
+  int tiles_env = 1;
+  if (const char* e = getenv("B2Z_EVALCHECK_TILES")) tiles_env = atoi(e);
+  //   MEASURED (B200, round 2, profiles/r2_evalcheck_variants.txt): the kernel itself gets 12 % faster (rv32im-scale, po2 20:
+  //   35.9 -> 31.4 ms) but the transpose moves 9.5 GB for it (3.8 ms) and holds 5.2 GB per context, and the block job gets
+  //   SLOWER (11.3 -> 8.4 M cycles/s, two segments in flight); on the 1 490-step planning program it is 3x slower (7.2 -> 22.5 ms).
+  //   A negative result: default OFF, B2Z_EVALCHECK_TILED=1 turns it on.
+  const bool tiled = parts_m > 0 && points_k == 1 && tiles_env <= 1 && getenv("B2Z_EVALCHECK_TILED") && getenv("B2Z_EVALCHECK_TILED")[0] == '1';
+  if (tiled)
+    o << "// tap load from the tiled LDE copy: `p` = this thread's row pointer + a compile-time offset (folded into the LDG immediate)\n"
+         "__device__ __forceinline__ u32 ldt(const char* p) { u32 v; asm volatile(\"ld.global.nc.u32 %0, [%1];\" : \"=r\"(v) : \"l\"(p)); return v; }\n";
+  const unsigned tile_halo = 4 * max_back, tile_pitch_bytes = 4 * (128 + tile_halo);
+  const size_t tws[3] = {c->group_size[0] ? c->group_size[0] : 1, c->group_size[1] ? c->group_size[1] : 1, c->group_size[2] ? c->group_size[2] : 1};
+  const size_t tile_ncol = tws[0] + tws[1] + tws[2];
+  c->eval_tiled = false;
+  const std::string wib_args = ib_args, wib_params = ib_params;  // the witgen parts keep their row offsets
   // B2Z_EVALCHECK_STAGED=1 selects the shared-memory-staged form (codegen_eval_staged).  Measured on B200 (rv32im-scale program,
   // po2 20): per-use global loads 35.7 ms, staged G = 8 / 6 / 4 groups 41.9 / 41.4 / 44.2 ms; planning circuit 1.84 vs 3.95 ms.
   // ncu of the staged kernel (profiles/r2_prof_evalcheck_staged_ncu.txt): DRAM reads 1.08 GB instead of 16.5 GB, 24 % fewer
@@ -895,6 +923,13 @@ void circuit_codegen(b2z_circuit* c) {
     em.cp_name = cpn;
     em.kc_name = kcn;
     if (parts_m > 0) em.stmts = &stmts;
+    if (tiled) {
+      em.tiled = true;
+      em.tile_flat0[0] = 0;
+      em.tile_flat0[1] = tws[0];
+      em.tile_flat0[2] = tws[0] + tws[1];
+      em.tile_pitch_bytes = tile_pitch_bytes;
+    }
     // A mix variable = its accumulated `tot` plus up to three constraints not folded in yet.  Constraint values are base-field
     // words, so a run of AndEqz steps adds pw[e] * val_e to each of the four components: four such terms are accumulated in
     // 64 bits and reduced once (dot4, 10 instructions per component) instead of four products + four modular adds (28).
@@ -974,8 +1009,13 @@ void circuit_codegen(b2z_circuit* c) {
   }
   // parts mode reads its tables from module __constant__ memory (ccp / ckc): the two structs must NOT also travel as kernel
   // parameters (a program of the rv32im size class has ~45 KB of poly_mix powers; the parameter space is 32 KB)
+  if (tiled) {
+    ib_args = "pt";
+    ib_params = "const char* pt";
+  }
   const std::string kernel_head_params =
-      parts_m > 0 ? std::string("u32* __restrict__ check, u32 iz0, u32 iz1, u32 iz2, u32 iz3, u64 mask")
+      tiled       ? std::string("u32* __restrict__ check, const char* __restrict__ tiled, u32 iz0, u32 iz1, u32 iz2, u32 iz3, u64 mask")
+      : parts_m > 0 ? std::string("u32* __restrict__ check, u32 iz0, u32 iz1, u32 iz2, u32 iz3, u64 mask")
                   : std::string("u32* __restrict__ check, const __grid_constant__ ColPtrs cp, const __grid_constant__ Consts kc, "
                                 "u32 iz0, u32 iz1, u32 iz2, u32 iz3, u64 mask");
   // B2Z_EVALCHECK_THREADS = T (parts mode, one point per thread): CTA size.  With T > 128 the CTA's warps are held together by a
@@ -1117,7 +1157,15 @@ void circuit_codegen(b2z_circuit* c) {
         // every thread must reach the barriers: out-of-range threads (domains smaller than a CTA) evaluate point `mask` and skip the store
         o << "  const u64 i0 = (u64)blockIdx.x * blockDim.x + threadIdx.x;\n  const u64 i = i0 > mask ? mask : i0;\n  const u64 domain = mask + 1;\n";
       }
-      for (unsigned b = 0; b <= max_back; b++) o << "  const u32 ib" << b << " = (u32)((i - " << 4 * b << "ull) & mask) << 2;\n";
+      if (tiled) {
+        o << "  const char* pt = tiled + (i >> 7) * " << (unsigned long long)tile_ncol * tile_pitch_bytes << "ull + ((" << tile_halo
+          << "u + (u32)(i & 127)) << 2);\n";
+        c->eval_tiled = true;
+        c->eval_tile_halo = tile_halo;
+        c->eval_tile_ncol = (unsigned)tile_ncol;
+      } else {
+        for (unsigned b = 0; b <= max_back; b++) o << "  const u32 ib" << b << " = (u32)((i - " << 4 * b << "ull) & mask) << 2;\n";
+      }
       if (cta_sync) {
         std::string body = main_body.str(), synced;
         size_t pos = 0, nl;
@@ -1241,7 +1289,7 @@ void circuit_codegen(b2z_circuit* c) {
         if (last_use_part.count(wst[k].id) && last_use_part[wst[k].id] > p) outs.push_back(wst[k].id);
       }
       o << "struct WR" << p << " { u32 v[" << (outs.empty() ? 1 : outs.size()) << "]; };\n";
-      o << "static __device__ __noinline__ WR" << p << " wpart" << p << "(" << ib_params;
+      o << "static __device__ __noinline__ WR" << p << " wpart" << p << "(" << wib_params;
       for (unsigned u : ins) o << ", u32 t" << u;
       o << ") {\n";
       for (size_t k = bounds[p]; k < bounds[p + 1]; k++) o << "  const u32 t" << wst[k].id << " = " << wst[k].expr << ";\n";
@@ -1249,7 +1297,7 @@ void circuit_codegen(b2z_circuit* c) {
       if (outs.empty()) o << "  r.v[0] = 0u;\n";
       for (size_t jj = 0; jj < outs.size(); jj++) o << "  r.v[" << jj << "] = t" << outs[jj] << ";\n";
       o << "  return r;\n}\n";
-      wmain << "  const WR" << p << " w" << p << " = wpart" << p << "(" << ib_args;
+      wmain << "  const WR" << p << " w" << p << " = wpart" << p << "(" << wib_args;
       for (unsigned u : ins) wmain << ", t" << u;
       wmain << ");\n";
       for (size_t jj = 0; jj < outs.size(); jj++) wmain << "  const u32 t" << outs[jj] << " = w" << p << ".v[" << jj << "];\n";

@@ -33,7 +33,9 @@ struct b2z_circuit {
   unsigned eval_threads = 128;                // CTA size of the generated eval_check (B2Z_EVALCHECK_THREADS)
   unsigned eval_tiles = 1;                    // tiles of eval_threads points per CTA (B2Z_EVALCHECK_TILES); state in shared memory
   size_t eval_smem_bytes = 0;
-  unsigned eval_points_per_cta = 0;           // staged eval_check: coset points per CTA (0: threads * points * tiles)
+  unsigned eval_points_per_cta = 0;
+  bool eval_tiled = false;                    // eval_check reads a tiled copy of the LDE matrices (built per launch)
+  unsigned eval_tile_halo = 0, eval_tile_ncol = 0;           // staged eval_check: coset points per CTA (0: threads * points * tiles)
   unsigned points_per_thread = 1;             // coset points per thread of the generated eval_check (parts mode, B2Z_EVALCHECK_POINTS)
   void *ccp_dev = nullptr, *ckc_dev = nullptr;  // device addresses of the module's __constant__ tables (parts mode)
   void *wcp_dev = nullptr, *wglobals_dev = nullptr;  // witgen: trace column pointers and the globals pointer (parts mode)

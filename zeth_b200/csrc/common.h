@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <map>
 #include <string>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/b2z.h"
@@ -49,6 +50,7 @@ struct b2z_ctx {
   std::vector<cudaEvent_t> stage_events;
   bool last_upload_staged = false;
   uint64_t launches = 0;
+  cudaEvent_t wait_event = nullptr;            // cudaEventBlockingSync event behind b2z::stream_wait
   // per-size device table, built lazily: 3^rev(j) for zk_shift (NTT twist tables live in kernels_ntt.cu's registry)
   uint32_t* pow3rev[b2z::MAX_PO2 + 1] = {};
   cudaStream_t aux_stream = nullptr;           // second launch stream of the role-split hash kernels (fork / join by events)
@@ -63,6 +65,22 @@ struct b2z_ctx {
 };
 
 namespace b2z {
+
+// Host wait for everything enqueued on `s`: an OS-blocking wait on a cudaEventBlockingSync event instead of
+// cudaStreamSynchronize's spin loop.  A session runs `in_flight` worker threads per GPU and a node runs one process per
+// GPU: spinning waits would burn 2 x 8 cores (and, inside a CPU-quota cgroup, get every thread of the process throttled).
+// B2Z_SPIN_SYNC=1 restores the spinning wait.
+inline cudaError_t stream_wait(b2z_ctx* ctx, cudaStream_t s) {
+  static const bool spin = [] { const char* e = getenv("B2Z_SPIN_SYNC"); return e && e[0] == '1'; }();
+  if (spin) return cudaStreamSynchronize(s);
+  if (!ctx->wait_event) {
+    cudaError_t e = cudaEventCreateWithFlags(&ctx->wait_event, cudaEventBlockingSync | cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
+  }
+  cudaError_t e = cudaEventRecord(ctx->wait_event, s);
+  if (e != cudaSuccess) return e;
+  return cudaEventSynchronize(ctx->wait_event);
+}
 
 // ---- kernel launchers (kernels_*.cu); all enqueue on ctx->stream and bump ctx->launches ----
 b2z_err ensure_tables(b2z_ctx* ctx, unsigned po2, bool pow3);

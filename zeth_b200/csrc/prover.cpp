@@ -163,7 +163,7 @@ static b2z_err poly_group_finish(b2z_ctx* ctx, DevMem& mem, PolyGroupDev& pg, un
   B2Z_CUDA(cudaMemcpyAsync(seal.w + seal.pos, pg.nodes + 8 * mp.top_size, 32 * mp.top_size, cudaMemcpyDeviceToHost, ctx->stream));
   uint32_t* root = seal.w + seal.cap;  // scratch after the seal image (ensure_pinned reserves 64 extra words)
   B2Z_CUDA(cudaMemcpyAsync(root, pg.nodes + 8, 32, cudaMemcpyDeviceToHost, ctx->stream));
-  B2Z_CUDA(cudaStreamSynchronize(ctx->stream));
+  B2Z_CUDA(b2z::stream_wait(ctx, ctx->stream));
   seal.pos += 8 * mp.top_size;
   rng.mix(root);
   return nullptr;
@@ -376,7 +376,7 @@ b2z_err prove_segment_device(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, c
   }
   Fp4* eval_u = reinterpret_cast<Fp4*>(scratch + 8);
   B2Z_CUDA(cudaMemcpyAsync(eval_u, evals_dev, 16 * n_evals, cudaMemcpyDeviceToHost, ctx->stream));
-  B2Z_CUDA(cudaStreamSynchronize(ctx->stream));
+  B2Z_CUDA(b2z::stream_wait(ctx, ctx->stream));
   B2Z_REQUIRE(seal.pos + 4 * n_evals <= seal.cap, "seal overflow");
   Fp4* coeff_u = reinterpret_cast<Fp4*>(seal.w + seal.pos);
   for (size_t r = 0; r < n_regs; r++) {
@@ -485,7 +485,7 @@ b2z_err prove_segment_device(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, c
     B2Z_REQUIRE(seal.pos + 8 * mp.top_size <= seal.cap, "seal overflow");
     B2Z_CUDA(cudaMemcpyAsync(seal.w + seal.pos, r.nodes + 8 * mp.top_size, 32 * mp.top_size, cudaMemcpyDeviceToHost, ctx->stream));
     B2Z_CUDA(cudaMemcpyAsync(scratch, r.nodes + 8, 32, cudaMemcpyDeviceToHost, ctx->stream));
-    B2Z_CUDA(cudaStreamSynchronize(ctx->stream));
+    B2Z_CUDA(b2z::stream_wait(ctx, ctx->stream));
     B2Z_TRY(check_remainders());
     seal.pos += 8 * mp.top_size;
     rng.mix(scratch);
@@ -504,7 +504,7 @@ b2z_err prove_segment_device(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, c
     B2Z_TRY(launch_bit_reverse(ctx, fin, 4, ilog2(size)));
     B2Z_REQUIRE(seal.pos + 4 * size <= seal.cap, "seal overflow");
     B2Z_CUDA(cudaMemcpyAsync(seal.w + seal.pos, fin, 16 * size, cudaMemcpyDeviceToHost, ctx->stream));
-    B2Z_CUDA(cudaStreamSynchronize(ctx->stream));
+    B2Z_CUDA(b2z::stream_wait(ctx, ctx->stream));
     B2Z_TRY(check_remainders());
     host_hash_elem_slice(seal.w + seal.pos, 4 * size, dg);
     seal.pos += 4 * size;
@@ -546,7 +546,7 @@ b2z_err prove_segment_device(b2z_ctx* ctx, const b2z_circuit* c, unsigned po2, c
   }
   tm.end(9);
   tm.end(10);
-  B2Z_CUDA(cudaStreamSynchronize(ctx->stream));
+  B2Z_CUDA(b2z::stream_wait(ctx, ctx->stream));
   tm.collect();
   if (const char* tr = getenv("B2Z_TRACE")) {
     // one JSON line per segment on stderr (field names follow the reference harness: run-parallel.sh:15 `total_cycles`)
@@ -833,7 +833,7 @@ b2z_err compute_control_root(b2z_ctx* ctx, unsigned po2, const uint32_t* code_de
   B2Z_TRY(launch_evaluate(ctx, evaluated, coeffs, cols, po2 + 2, 2));
   B2Z_TRY(merkle_build(ctx, nodes, evaluated, domain, cols));
   B2Z_CUDA(cudaMemcpyAsync(root_host, nodes + 8, 32, cudaMemcpyDeviceToHost, ctx->stream));
-  B2Z_CUDA(cudaStreamSynchronize(ctx->stream));
+  B2Z_CUDA(b2z::stream_wait(ctx, ctx->stream));
   return nullptr;
 }
 

@@ -439,7 +439,7 @@ b2z_err b2z_prove_session(b2z_session* s, const b2z_segment_input* segs, size_t 
         if (strstr(e, "does not satisfy")) break;
         if (attempt == 0) {
           retries.fetch_add(1);
-          cudaStreamSynchronize(w.ctx->stream);
+          b2z::stream_wait(w.ctx, w.ctx->stream);
           cudaGetLastError();
         }
       }

@@ -85,3 +85,79 @@ def all_gather_seals(local_seals: list, n_total: int, seal_words: int, device: t
         return None
     host = allg.cpu().numpy().view(np.uint32)
     return [host[(i % world) * per_rank + i // world] for i in range(n_total)]
+
+
+def _gather_indexed(done: dict, n_total: int, seal_words: int, device: torch.device) -> list[np.ndarray] | None:
+    """Gather {segment index: seal} of irregular shares (after a re-assignment): rows of [index, seal words], -1 = padding."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    cnt = torch.tensor([len(done)], dtype=torch.int64, device=device)
+    dist.all_reduce(cnt, op=dist.ReduceOp.MAX)
+    rows = int(cnt.item())
+    stage = torch.full((rows, 1 + seal_words), -1, dtype=torch.int32)
+    st = stage.numpy()
+    for k, (i, s) in enumerate(sorted(done.items())):
+        st[k, 0] = i
+        st[k, 1:] = np.asarray(s, dtype=np.uint32).view(np.int32)
+    allg = torch.empty((world * rows, 1 + seal_words), dtype=torch.int32, device=device)
+    dist.all_gather_into_tensor(allg, stage.to(device))
+    if rank != 0:
+        return None
+    host = allg.cpu().numpy()
+    seals: list = [None] * n_total
+    for row in host:
+        if row[0] >= 0:
+            seals[int(row[0])] = row[1:].view(np.uint32).copy()
+    missing = [i for i, s in enumerate(seals) if s is None]
+    if missing:
+        raise RuntimeError(f"seals of segments {missing} are missing after the gather")
+    return seals
+
+
+def prove_sharded(n_total: int, prove_fn, seal_words: int, device: torch.device, max_attempts: int = 2):
+    """The N-GPU session: segment i -> rank i mod world, every rank proves its share with `prove_fn(indices) -> [seal, ...]`
+    (b2z_prove_session on that rank's GPU), rank 0 gets the seals back in segment order.
+
+    Failure handling (upstream has none -- a failed segment fails `prove_session`; a node of 8 GPUs should not lose a block's
+    session to one bad device): b2z_prove_session already retries a device error once on the same GPU; if a rank's
+    `prove_fn` still raises, that rank's whole share is re-assigned round-robin to the ranks that succeeded and proved
+    there (one extra collective, a MAX all-reduce of the per-segment failure flags, per attempt).  When no attempt is left
+    or no healthy rank exists, every rank raises the same error.  Returns (seals in order on rank 0 / None elsewhere,
+    number of segments that were re-assigned)."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    if world == 1:
+        return [np.asarray(s, dtype=np.uint32) for s in prove_fn(list(range(n_total)))], 0
+    todo = partition(n_total, world, rank)
+    done: dict[int, np.ndarray] = {}
+    reassigned = 0
+    bad_ranks: set[int] = set()
+    for attempt in range(max_attempts):
+        failed_here, why = [], ""
+        if todo:
+            try:
+                seals = prove_fn(todo)
+                if len(seals) != len(todo):
+                    raise RuntimeError(f"prove_fn returned {len(seals)} seals for {len(todo)} segments")
+                done.update(zip(todo, seals))
+            except Exception as e:  # noqa: BLE001 -- any failure of this rank's prover re-assigns its share
+                failed_here, why = todo, f"{type(e).__name__}: {e}"
+        flags = torch.zeros(n_total + world, dtype=torch.int32, device=device)
+        for i in failed_here:
+            flags[i] = 1
+        if failed_here:
+            flags[n_total + rank] = 1
+        dist.all_reduce(flags, op=dist.ReduceOp.MAX)
+        flags = flags.cpu().numpy()
+        failed = [int(i) for i in np.nonzero(flags[:n_total])[0]]
+        if not failed:
+            break
+        bad_ranks |= {r for r in range(world) if flags[n_total + r]}
+        healthy = [r for r in range(world) if r not in bad_ranks]
+        if attempt + 1 == max_attempts or not healthy:
+            raise RuntimeError(f"segments {failed} failed on rank(s) {sorted(bad_ranks)} and could not be re-assigned"
+                               + (f" (this rank: {why})" if why else ""))
+        todo = [seg for k, seg in enumerate(failed) if healthy[k % len(healthy)] == rank]
+        reassigned += len(failed)
+    if reassigned == 0:
+        return all_gather_seals([done[i] for i in partition(n_total, world, rank)], n_total, seal_words, device), 0
+    return _gather_indexed(done, n_total, seal_words, device), reassigned
