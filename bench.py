@@ -597,11 +597,15 @@ def run_block_workload(args):
         assert rc == 0, f"Receipt::verify failed with code {rc} at segment {bad}"
         verified = nchk
         full.close()
-    per_seg_ms = None
+    per_seg_ms, lat_stats = None, None
     if rank == 0:
         buf = (__import__("ctypes").c_double * 4096)()
         cnt = int(sess.L.b2z_session_last_segment_ms(sess.h, buf, 4096))
-        per_seg_ms = float(np.median([buf[i] for i in range(min(cnt, 4096))])) if cnt else None
+        lat = np.array([buf[i] for i in range(min(cnt, 4096))], dtype=np.float64)
+        per_seg_ms = float(np.median(lat)) if cnt else None
+        # diagnostic: sum / in_flight ~= wall time of the session call when the workers never idle; max >> median = outlier segments
+        lat_stats = {"p10": float(np.percentile(lat, 10)), "p90": float(np.percentile(lat, 90)), "max": float(lat.max()),
+                     "sum_over_in_flight": float(lat.sum() / max(1, args.in_flight))} if cnt else None
     for r in receipts:
         r.close()
 
@@ -678,7 +682,7 @@ def run_block_workload(args):
                        "parallelism": f"independent segments round-robin over {world} GPU(s); NCCL broadcast of the segment table, "
                                       f"all_gather of the seals (inside the timed region)",
                        "seal_gather_ms": gather_ms, "rank_prove_ms": rank_prove_ms, "segment_retries": retries, "segments_reassigned_across_ranks": reassigned, "receipt_verified_segments": verified,
-                       "median_segment_latency_ms": per_seg_ms, "phase_ms_per_segment": phase_ms,
+                       "median_segment_latency_ms": per_seg_ms, "segment_latency_ms": lat_stats, "phase_ms_per_segment": phase_ms,
                        "l2": "inputs >> L2 (0.87 GB of witness per segment), no flush needed",
                        "timing": "witnesses resident in HBM; barrier + synchronize, CUDA events around [prove_session + seal gather], "
                                  "max over ranks (== wall clock of the region)",
