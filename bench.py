@@ -531,7 +531,13 @@ def run_block_workload(args):
     wr.close()
     code0 = wit[0]["_t"][0] if wit else None
     del wit
-    wit = [gen(sg) for sg in timed_ids]
+    # (guard for very large K: at most ~55 % of HBM holds resident witnesses; beyond that the distinct witnesses are reused
+    #  cyclically -- every segment is still proved in full -- and config.distinct_witnesses_per_rank says so)
+    wit_bytes = 4 * (wc * n + wd * n + max(wa * zk, 1))
+    cap = max(2, int(0.55 * torch.cuda.get_device_properties(dev).total_memory / wit_bytes))
+    base = [gen(sg) for sg in timed_ids[:cap]]
+    wit = [dict(base[k % len(base)]) for k in range(len(timed_ids))]
+    distinct = len(base)
     for k, wt in enumerate(wit):
         wt["index"] = k
     if wit:  # (a rank may have no timed segment when K * S < world)
@@ -678,7 +684,7 @@ def run_block_workload(args):
                                    f"{S} consecutive segments ({S * n} cycles); job = {K} x {S} segments, segment i -> rank i mod {world}; "
                                    f"synthetic {sc.name.rstrip('_')} circuit W=256 (code 16 + data 192 + accum 48), zk rows {zk}",
                        "circuit": args.circuit, "circuit_steps": sc.n_steps, "circuit_taps": sc.n_taps, "po2": po2, "segments_per_step": S,
-                       "segments_total": n_timed, "cycles_total": n_timed * n, "in_flight_per_gpu": sess.in_flight,
+                       "segments_total": n_timed, "distinct_witnesses_per_rank": distinct, "cycles_total": n_timed * n, "in_flight_per_gpu": sess.in_flight,
                        "parallelism": f"independent segments round-robin over {world} GPU(s); NCCL broadcast of the segment table, "
                                       f"all_gather of the seals (inside the timed region)",
                        "seal_gather_ms": gather_ms, "rank_prove_ms": rank_prove_ms, "segment_retries": retries, "segments_reassigned_across_ranks": reassigned, "receipt_verified_segments": verified,
