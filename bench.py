@@ -71,6 +71,7 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.skip = 0
 
     def start(self):
         try:
@@ -85,6 +86,12 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self):
+        """The timed region starts now: only samples taken from here on are reported.  The sampler itself is started BEFORE
+        the warm-up, because nvidia-smi's start-up (NVML attaching to every GPU of the node) takes driver locks that can stall
+        kernel launches of the process it watches for ~0.2 s -- an artefact that must not land inside the timed region."""
+        self.skip = len(self.lines)
+
     def stop(self) -> dict:
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -95,7 +102,7 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in self.lines[self.skip:]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -263,20 +270,21 @@ def run_segment_workload(args):
         return d_glob.cpu().numpy().view(np.uint32)[: sc.globals_size].copy()
 
     seals = {}
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     # ---- warm-up ----
     for seg in mine[:W]:
         g = gen(seg)
         seals[seg] = hal.prove_segment_device(circuit, po2, d_code.data_ptr(), d_data.data_ptr(), g, d_noise.data_ptr(), zk)
     # ---- timed: K segment proofs, witness resident in HBM (each >> L2: 3.3 GiB witness at po2 22; no L2 flush needed) ----
     launches0 = hal.launch_count()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     step_ms = []
     phase_acc = {}
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    sampler.mark()
     total_ms = 0.0
     witgen_launches = 0
     for seg in mine[W:]:
@@ -514,6 +522,9 @@ def run_block_workload(args):
                     on_device=True, _t=(code, data, noise), seg=seg)
 
     torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     # ---- warm-up: W slices (untimed) ----
     wit = [gen(sg) for sg in warm_ids]
     for k, wt in enumerate(wit):
@@ -556,13 +567,11 @@ def run_block_workload(args):
         return [r.seal(k) for k in range(r.n_segments)]
 
     launches0 = sess.launch_count()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
 
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()
