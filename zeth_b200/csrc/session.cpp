@@ -76,10 +76,15 @@ b2z_err receipt_assemble(const b2z_circuit* c, const uint32_t* const* seals, con
   b2z_receipt* r = (b2z_receipt*)calloc(1, sizeof(b2z_receipt));
   B2Z_REQUIRE(r, "out of memory");
   r->segments = (b2z_segment_receipt*)calloc(n ? n : 1, sizeof(b2z_segment_receipt));
-  r->n_segments = n;
+  r->n_segments = r->segments ? n : 0;
   verifier_parameters(c, r->verifier_parameters);
+  if (journal_len) r->journal = (uint8_t*)malloc(journal_len);
+  if (!r->segments || (journal_len && (!r->journal || !journal))) {
+    free_receipt_contents(r);
+    free(r);
+    return set_error(journal_len && !journal ? "receipt_assemble: null journal" : "out of memory");
+  }
   if (journal_len) {
-    r->journal = (uint8_t*)malloc(journal_len);
     memcpy(r->journal, journal, journal_len);
     r->journal_len = journal_len;
   }
@@ -94,6 +99,11 @@ b2z_err receipt_assemble(const b2z_circuit* c, const uint32_t* const* seals, con
       return set_error("receipt_assemble: seal " + std::to_string(i) + " is shorter than its header");
     }
     s.seal = (uint32_t*)malloc(4 * seal_words[i]);
+    if (!s.seal) {
+      free_receipt_contents(r);
+      free(r);
+      return set_error("out of memory");
+    }
     memcpy(s.seal, seals[i], 4 * seal_words[i]);
     s.seal_words = seal_words[i];
   }
@@ -226,10 +236,12 @@ b2z_err receipt_deserialize(const uint8_t* bytes, size_t len, b2z_receipt** out)
   if (!rd.ok || jlen > len - rd.pos || nseg > (len - rd.pos) / 128 + 1) return fail("receipt: truncated header");
   if (jlen) {
     r->journal = (uint8_t*)malloc(jlen);
+    if (!r->journal) return fail("out of memory");
     rd.bytes(r->journal, jlen);
     r->journal_len = jlen;
   }
   r->segments = (b2z_segment_receipt*)calloc(nseg ? nseg : 1, sizeof(b2z_segment_receipt));
+  if (!r->segments) return fail("out of memory");
   for (uint64_t i = 0; i < nseg; i++) {
     b2z_segment_receipt& s = r->segments[i];
     r->n_segments = i + 1;
@@ -243,6 +255,7 @@ b2z_err receipt_deserialize(const uint8_t* bytes, size_t len, b2z_receipt** out)
     uint64_t sw = rd.u64();
     if (!rd.ok || sw > (len - rd.pos) / 4) return fail("receipt: truncated segment");
     s.seal = (uint32_t*)malloc(sw ? 4 * sw : 4);
+    if (!s.seal) return fail("out of memory");
     rd.words(s.seal, sw);
     s.seal_words = sw;
   }
