@@ -6,7 +6,7 @@
  * un-vendored risc0 crates drive a `Hal` / `CircuitHal` back-end whose CUDA implementation crosses an
  * `extern "C"` boundary into risc0-sys kernels.  This header is that boundary for the B200 back-end: plain
  * pointers and sizes, no C++ / torch types.  Each entry point names the upstream trait method it replaces
- * (risc0-zkp 3.0.2 `hal/mod.rs` trait Hal, `prove/*.rs`; risc0-circuit-rv32im 4.0.2 CircuitHal), which is what a
+ * (risc0-zkp 3.0.2 `hal/mod.rs` trait Hal, the `prove/` modules; risc0-circuit-rv32im 4.0.2 CircuitHal), which is what a
  * Rust `impl Hal for B200Hal` shim binds.
  *
  * Conventions (same as upstream's FFI): every function returns NULL on success or a NUL-terminated error string.
