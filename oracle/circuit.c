@@ -240,9 +240,10 @@ void or_circuit_free(or_circuit *c) {
   free(c);
 }
 
-/* ---- prover-side evaluation (typed: base-field values stay base-field) ---- */
-void or_eval_check(const or_circuit *c, fp *check, const fp *const groups[3], const fp *globals, const fp *mix,
-                   const fp4 *poly_mix, unsigned po2) {
+/* ---- prover-side evaluation, plain form: one point at a time, every value an fp4 (the definition; the lane-blocked form
+ * below must agree with it bit for bit -- tests/test_oracle_circuit.py) ---- */
+void or_eval_check_scalar(const or_circuit *c, fp *check, const fp *const groups[3], const fp *globals, const fp *mix,
+                          const fp4 *poly_mix, unsigned po2) {
   size_t n = (size_t)1 << po2, domain = 4 * n, mask = domain - 1;
   fp4 *pows = (fp4 *)malloc(sizeof(fp4) * (c->max_exp + 2));
   pows[0] = fp4_one();
@@ -306,6 +307,253 @@ void or_eval_check(const or_circuit *c, fp *check, const fp *const groups[3], co
     free(mxv);
   }
   free(pows);
+}
+
+/* ---- prover-side evaluation, the form the CPU baseline runs: the same program, statically typed (base-field values
+ * cost one word and one operation, not four), evaluated on LANES consecutive points at a time so that every field
+ * operation is a loop over lanes the compiler vectorises, with value slots recycled at their last use so that the working
+ * set stays in cache.  This is the stand-in for upstream's ahead-of-time compiled `poly_fp` (risc0-circuit-rv32im
+ * generates straight-line C++ / CUDA from the same step list); exact field arithmetic, so results are identical to
+ * or_eval_check_scalar. ---- */
+#define LANES 16
+enum {
+  F_CONST_B, F_CONST_E, F_GET, F_GLOBAL,
+  F_ADD_BB, F_ADD_EB, F_ADD_EE, F_SUB_BB, F_SUB_EB, F_SUB_BE, F_SUB_EE, F_MUL_BB, F_MUL_EB, F_MUL_EE,
+  F_TRUE, F_EQZ_B, F_EQZ_E, F_COND_B, F_COND_E
+};
+typedef struct {
+  uint32_t op, o, a, b, c; /* slots (base / ext / mix array according to op); F_GET: a = tap; F_GLOBAL: a, b as in the step */
+  fp imm[4];               /* constants (Montgomery) */
+  uint32_t exp;            /* power of poly_mix of AndEqz / AndCond */
+} fstep_t;
+typedef struct {
+  uint32_t *free_list, n_free, n_slots;
+} slot_pool;
+static uint32_t slot_take(slot_pool *p) { return p->n_free ? p->free_list[--p->n_free] : p->n_slots++; }
+static void slot_give(slot_pool *p, uint32_t s) { p->free_list[p->n_free++] = s; }
+
+typedef fp lane_t[LANES];
+static inline void l_add(fp *restrict o, const fp *a, const fp *b) {
+  for (int l = 0; l < LANES; l++) o[l] = fp_add(a[l], b[l]);
+}
+static inline void l_sub(fp *restrict o, const fp *a, const fp *b) {
+  for (int l = 0; l < LANES; l++) o[l] = fp_sub(a[l], b[l]);
+}
+static inline void l_mul(fp *restrict o, const fp *a, const fp *b) {
+  for (int l = 0; l < LANES; l++) o[l] = fp_mul(a[l], b[l]);
+}
+static inline void l_mulc(fp *restrict o, const fp *a, fp k) {
+  for (int l = 0; l < LANES; l++) o[l] = fp_mul(a[l], k);
+}
+static inline void l_copy(fp *restrict o, const fp *a) {
+  for (int l = 0; l < LANES; l++) o[l] = a[l];
+}
+/* ext x ext over lanes: o (4 lane rows) = a * b; o must not alias a or b */
+static inline void l_mul_ee(lane_t *restrict o, const lane_t *a, const lane_t *b) {
+  for (int l = 0; l < LANES; l++) {
+    fp4 x = {{a[0][l], a[1][l], a[2][l], a[3][l]}}, y = {{b[0][l], b[1][l], b[2][l], b[3][l]}};
+    fp4 r = fp4_mul(x, y);
+    o[0][l] = r.e[0]; o[1][l] = r.e[1]; o[2][l] = r.e[2]; o[3][l] = r.e[3];
+  }
+}
+/* ext lanes x one ext constant */
+static inline void l_mul_ec(lane_t *restrict o, const lane_t *a, fp4 k) {
+  for (int l = 0; l < LANES; l++) {
+    fp4 x = {{a[0][l], a[1][l], a[2][l], a[3][l]}};
+    fp4 r = fp4_mul(x, k);
+    o[0][l] = r.e[0]; o[1][l] = r.e[1]; o[2][l] = r.e[2]; o[3][l] = r.e[3];
+  }
+}
+
+void or_eval_check(const or_circuit *c, fp *check, const fp *const groups[3], const fp *globals, const fp *mix,
+                   const fp4 *poly_mix, unsigned po2) {
+  size_t n = (size_t)1 << po2, domain = 4 * n, mask = domain - 1;
+  if (domain < LANES) {
+    or_eval_check_scalar(c, check, groups, globals, mix, poly_mix, po2);
+    return;
+  }
+  /* ---- typed program with recycled slots ---- */
+  const size_t ns = c->n_steps;
+  uint32_t *last_fp = (uint32_t *)malloc((c->n_fp + 1) * 4), *last_mx = (uint32_t *)malloc((c->n_mix + 1) * 4);
+  memset(last_fp, 0xff, (c->n_fp + 1) * 4); /* 0xffffffff = never read */
+  memset(last_mx, 0xff, (c->n_mix + 1) * 4);
+  {
+    size_t nf = 0, nm = 0;
+    for (size_t k = 0; k < ns; k++) {
+      const step_t *s = &c->steps[k];
+      switch (s->op) {
+        case OP_ADD: case OP_SUB: case OP_MUL: last_fp[s->a] = (uint32_t)k; last_fp[s->b] = (uint32_t)k; nf++; break;
+        case OP_TRUE: nm++; break;
+        case OP_AND_EQZ: last_mx[s->a] = (uint32_t)k; last_fp[s->b] = (uint32_t)k; nm++; break;
+        case OP_AND_COND: last_mx[s->a] = (uint32_t)k; last_fp[s->b] = (uint32_t)k; last_mx[s->c] = (uint32_t)k; nm++; break;
+        default: nf++; break;
+      }
+    }
+    (void)nf; (void)nm;
+    last_mx[c->ret] = (uint32_t)ns; /* read after the program */
+  }
+  fstep_t *prog = (fstep_t *)calloc(ns + 1, sizeof(fstep_t));
+  uint32_t *slot_fp = (uint32_t *)calloc(c->n_fp + 1, 4), *slot_mx = (uint32_t *)calloc(c->n_mix + 1, 4);
+  slot_pool pb = {(uint32_t *)calloc(c->n_fp + 1, 4), 0, 0}, pe = {(uint32_t *)calloc(c->n_fp + 1, 4), 0, 0},
+            pm = {(uint32_t *)calloc(c->n_mix + 1, 4), 0, 0};
+  {
+    size_t nf = 0, nm = 0;
+    for (size_t k = 0; k < ns; k++) {
+      const step_t *s = &c->steps[k];
+      fstep_t *f = &prog[k];
+      const int is_fp_out = s->op <= OP_MUL;
+      if (is_fp_out) {
+        const int ext = c->fp_is_ext[nf];
+        f->o = slot_take(ext ? &pe : &pb);
+        slot_fp[nf] = f->o;
+      } else {
+        f->o = slot_take(&pm);
+        slot_mx[nm] = f->o;
+      }
+      switch (s->op) {
+        case OP_CONST: f->op = F_CONST_B; f->imm[0] = fp_from_u32(s->a); break;
+        case OP_CONST_EXT:
+          f->op = F_CONST_E;
+          f->imm[0] = fp_from_u32(s->a); f->imm[1] = fp_from_u32(s->b); f->imm[2] = fp_from_u32(s->c); f->imm[3] = fp_from_u32(s->d);
+          break;
+        case OP_GET: f->op = F_GET; f->a = s->a; break;
+        case OP_GET_GLOBAL: f->op = F_GLOBAL; f->a = s->a; f->b = s->b; break;
+        case OP_ADD: case OP_SUB: case OP_MUL: {
+          const int ea = c->fp_is_ext[s->a], eb = c->fp_is_ext[s->b];
+          f->a = slot_fp[s->a]; f->b = slot_fp[s->b];
+          if (s->op == OP_SUB) {
+            f->op = !ea && !eb ? F_SUB_BB : ea && !eb ? F_SUB_EB : !ea && eb ? F_SUB_BE : F_SUB_EE;
+          } else {
+            const uint32_t bb = s->op == OP_ADD ? F_ADD_BB : F_MUL_BB, eb_ = s->op == OP_ADD ? F_ADD_EB : F_MUL_EB,
+                           ee = s->op == OP_ADD ? F_ADD_EE : F_MUL_EE;
+            if (!ea && !eb) f->op = bb;
+            else if (ea && eb) f->op = ee;
+            else {
+              f->op = eb_;            /* commutative: put the ext operand first */
+              if (!ea) { uint32_t t = f->a; f->a = f->b; f->b = t; }
+            }
+          }
+        } break;
+        case OP_TRUE: f->op = F_TRUE; break;
+        case OP_AND_EQZ:
+          f->op = c->fp_is_ext[s->b] ? F_EQZ_E : F_EQZ_B;
+          f->a = slot_mx[s->a]; f->b = slot_fp[s->b]; f->exp = c->mix_exp[s->a];
+          break;
+        case OP_AND_COND:
+          f->op = c->fp_is_ext[s->b] ? F_COND_E : F_COND_B;
+          f->a = slot_mx[s->a]; f->b = slot_fp[s->b]; f->c = slot_mx[s->c]; f->exp = c->mix_exp[s->a];
+          break;
+      }
+      /* operands that die here give their slots back (after the output slot was taken: no aliasing inside a step) */
+      if (s->op == OP_ADD || s->op == OP_SUB || s->op == OP_MUL) {
+        if (last_fp[s->a] == k) slot_give(c->fp_is_ext[s->a] ? &pe : &pb, slot_fp[s->a]);
+        if (s->b != s->a && last_fp[s->b] == k) slot_give(c->fp_is_ext[s->b] ? &pe : &pb, slot_fp[s->b]);
+      } else if (s->op == OP_AND_EQZ || s->op == OP_AND_COND) {
+        if (last_mx[s->a] == k) slot_give(&pm, slot_mx[s->a]);
+        if (last_fp[s->b] == k) slot_give(c->fp_is_ext[s->b] ? &pe : &pb, slot_fp[s->b]);
+        if (s->op == OP_AND_COND && s->c != s->a && last_mx[s->c] == k) slot_give(&pm, slot_mx[s->c]);
+      }
+      /* a value nobody reads gives its slot back at once */
+      if (is_fp_out) {
+        if (last_fp[nf] == 0xffffffffu) slot_give(c->fp_is_ext[nf] ? &pe : &pb, f->o);
+        nf++;
+      } else {
+        if (last_mx[nm] == 0xffffffffu) slot_give(&pm, f->o);
+        nm++;
+      }
+    }
+  }
+  const uint32_t ret_slot = slot_mx[c->ret];
+  const size_t nb_slots = pb.n_slots + 1, ne_slots = pe.n_slots + 1, nm_slots = pm.n_slots + 1;
+  free(last_fp); free(last_mx); free(slot_fp); free(slot_mx); free(pb.free_list); free(pe.free_list); free(pm.free_list);
+
+  fp4 *pows = (fp4 *)malloc(sizeof(fp4) * (c->max_exp + 2));
+  pows[0] = fp4_one();
+  for (size_t i = 1; i <= c->max_exp + 1; i++) pows[i] = fp4_mul(pows[i - 1], *poly_mix);
+  fp three_n = fp_pow(fp_from_u32(3), n);
+  fp w4 = bb_rou_fwd(2);
+  fp inv_zero[4];
+  for (int k = 0; k < 4; k++) inv_zero[k] = fp_inv(fp_sub(fp_mul(three_n, fp_pow(w4, (uint64_t)k)), FP_ONE));
+  const fp *args[2] = {globals, mix};
+#pragma omp parallel
+  {
+    lane_t *B = (lane_t *)aligned_alloc(64, sizeof(lane_t) * nb_slots);
+    lane_t *E = (lane_t *)aligned_alloc(64, sizeof(lane_t) * 4 * ne_slots);
+    lane_t *M = (lane_t *)aligned_alloc(64, sizeof(lane_t) * 4 * nm_slots);
+    lane_t T[4], U[4];
+#pragma omp for schedule(static)
+    for (size_t i = 0; i < domain; i += LANES) {
+      for (size_t k = 0; k < ns; k++) {
+        const fstep_t *f = &prog[k];
+        switch (f->op) {
+          case F_CONST_B: for (int l = 0; l < LANES; l++) B[f->o][l] = f->imm[0]; break;
+          case F_CONST_E:
+            for (int q = 0; q < 4; q++)
+              for (int l = 0; l < LANES; l++) E[4 * f->o + q][l] = f->imm[q];
+            break;
+          case F_GET: {
+            const uint32_t t = f->a;
+            const fp *col = groups[c->tap_group[t]] + (size_t)c->tap_offset[t] * domain;
+            const size_t j0 = (i - 4 * (size_t)c->tap_back[t]) & mask;
+            if (j0 + LANES <= domain) l_copy(B[f->o], col + j0);
+            else
+              for (int l = 0; l < LANES; l++) B[f->o][l] = col[(j0 + (size_t)l) & mask];
+          } break;
+          case F_GLOBAL: { const fp g = args[f->a][f->b]; for (int l = 0; l < LANES; l++) B[f->o][l] = g; } break;
+          case F_ADD_BB: l_add(B[f->o], B[f->a], B[f->b]); break;
+          case F_SUB_BB: l_sub(B[f->o], B[f->a], B[f->b]); break;
+          case F_MUL_BB: l_mul(B[f->o], B[f->a], B[f->b]); break;
+          case F_ADD_EB: /* ext a + base b */
+            l_add(E[4 * f->o], E[4 * f->a], B[f->b]);
+            for (int q = 1; q < 4; q++) l_copy(E[4 * f->o + q], E[4 * f->a + q]);
+            break;
+          case F_SUB_EB: /* ext a - base b */
+            l_sub(E[4 * f->o], E[4 * f->a], B[f->b]);
+            for (int q = 1; q < 4; q++) l_copy(E[4 * f->o + q], E[4 * f->a + q]);
+            break;
+          case F_SUB_BE: /* base a - ext b */
+            l_sub(E[4 * f->o], B[f->a], E[4 * f->b]);
+            for (int q = 1; q < 4; q++)
+              for (int l = 0; l < LANES; l++) E[4 * f->o + q][l] = fp_neg(E[4 * f->b + q][l]);
+            break;
+          case F_ADD_EE: for (int q = 0; q < 4; q++) l_add(E[4 * f->o + q], E[4 * f->a + q], E[4 * f->b + q]); break;
+          case F_SUB_EE: for (int q = 0; q < 4; q++) l_sub(E[4 * f->o + q], E[4 * f->a + q], E[4 * f->b + q]); break;
+          case F_MUL_EB: for (int q = 0; q < 4; q++) l_mul(E[4 * f->o + q], E[4 * f->a + q], B[f->b]); break;
+          case F_MUL_EE: l_mul_ee(&E[4 * f->o], (const lane_t *)&E[4 * f->a], (const lane_t *)&E[4 * f->b]); break;
+          case F_TRUE:
+            for (int q = 0; q < 4; q++)
+              for (int l = 0; l < LANES; l++) M[4 * f->o + q][l] = 0;
+            break;
+          case F_EQZ_B: { /* tot + pow * val */
+            const fp4 m = pows[f->exp];
+            for (int q = 0; q < 4; q++) {
+              l_mulc(T[q], B[f->b], m.e[q]);
+              l_add(M[4 * f->o + q], M[4 * f->a + q], T[q]);
+            }
+          } break;
+          case F_EQZ_E: {
+            l_mul_ec(T, (const lane_t *)&E[4 * f->b], pows[f->exp]);
+            for (int q = 0; q < 4; q++) l_add(M[4 * f->o + q], M[4 * f->a + q], T[q]);
+          } break;
+          case F_COND_B: { /* tot + (inner * cond) * pow */
+            for (int q = 0; q < 4; q++) l_mul(T[q], M[4 * f->c + q], B[f->b]);
+            l_mul_ec(U, (const lane_t *)T, pows[f->exp]);
+            for (int q = 0; q < 4; q++) l_add(M[4 * f->o + q], M[4 * f->a + q], U[q]);
+          } break;
+          case F_COND_E: {
+            l_mul_ee(T, (const lane_t *)&M[4 * f->c], (const lane_t *)&E[4 * f->b]);
+            l_mul_ec(U, (const lane_t *)T, pows[f->exp]);
+            for (int q = 0; q < 4; q++) l_add(M[4 * f->o + q], M[4 * f->a + q], U[q]);
+          } break;
+        }
+      }
+      for (int q = 0; q < 4; q++)
+        for (int l = 0; l < LANES; l++) check[(size_t)q * domain + i + (size_t)l] = fp_mul(M[4 * ret_slot + q][l], inv_zero[l & 3]);
+    }
+    free(B); free(E); free(M);
+  }
+  free(pows);
+  free(prog);
 }
 
 /* adapter.rs poly_ext: same program on extension-field tap evaluations; MixState{tot, mul} carried explicitly. */

@@ -131,17 +131,61 @@ void or_zk_shift(fp *io, size_t count, size_t n) {
 }
 
 /* hal/cpu.rs hash_rows: digest r = unpadded_hash(matrix[0][r], matrix[1][r], ...). */
-void or_hash_rows(uint32_t *out, const fp *matrix, size_t rows, size_t cols) {
+void or_hash_rows_scalar(uint32_t *out, const fp *matrix, size_t rows, size_t cols) {
   or_poseidon2_init();
 #pragma omp parallel for schedule(static)
   for (size_t r = 0; r < rows; r++) or_hash_elems_strided(matrix + r, cols, rows, out + 8 * r);
 }
+/* 16 consecutive rows per sponge (the matrix is column-major: 16 rows of a column are one contiguous load) */
+void or_hash_rows(uint32_t *out, const fp *matrix, size_t rows, size_t cols) {
+  or_poseidon2_init();
+  const size_t blocks = rows / P2_LANES;
+#pragma omp parallel for schedule(static)
+  for (size_t b = 0; b < blocks; b++) {
+    fp st[24][P2_LANES];
+    memset(st, 0, sizeof st);
+    const size_t r0 = b * P2_LANES;
+    size_t unmixed = 0;
+    for (size_t c = 0; c < cols; c++) {
+      memcpy(st[unmixed++], matrix + c * rows + r0, sizeof(fp) * P2_LANES);
+      if (unmixed == 16) {
+        or_poseidon2_mix_lanes(st);
+        unmixed = 0;
+      }
+    }
+    if (unmixed != 0 || cols == 0) {
+      for (size_t i = unmixed; i < 16; i++) memset(st[i], 0, sizeof(fp) * P2_LANES);
+      or_poseidon2_mix_lanes(st);
+    }
+    for (int l = 0; l < P2_LANES; l++)
+      for (int k = 0; k < 8; k++) out[8 * (r0 + (size_t)l) + k] = st[k][l];
+  }
+  for (size_t r = blocks * P2_LANES; r < rows; r++) or_hash_elems_strided(matrix + r, cols, rows, out + 8 * r);
+}
 
 /* hal/cpu.rs hash_fold: node[out_size + j] = hash_pair(node[in_size + 2j], node[in_size + 2j + 1]) */
-void or_hash_fold(uint32_t *nodes, size_t in_size, size_t out_size) {
+void or_hash_fold_scalar(uint32_t *nodes, size_t in_size, size_t out_size) {
   or_poseidon2_init();
 #pragma omp parallel for schedule(static)
   for (size_t j = 0; j < out_size; j++)
+    or_hash_pair(nodes + 8 * (in_size + 2 * j), nodes + 8 * (in_size + 2 * j + 1), nodes + 8 * (out_size + j));
+}
+void or_hash_fold(uint32_t *nodes, size_t in_size, size_t out_size) {
+  or_poseidon2_init();
+  const size_t blocks = out_size / P2_LANES;
+#pragma omp parallel for schedule(static)
+  for (size_t b = 0; b < blocks; b++) {
+    fp st[24][P2_LANES];
+    for (int l = 0; l < P2_LANES; l++) {
+      const uint32_t *pair = nodes + 8 * (in_size + 2 * (b * P2_LANES + (size_t)l)); /* 16 consecutive words: left ‖ right */
+      for (int k = 0; k < 16; k++) st[k][l] = pair[k];
+      for (int k = 16; k < 24; k++) st[k][l] = 0;
+    }
+    or_poseidon2_mix_lanes(st);
+    for (int l = 0; l < P2_LANES; l++)
+      for (int k = 0; k < 8; k++) nodes[8 * (out_size + b * P2_LANES + (size_t)l) + k] = st[k][l];
+  }
+  for (size_t j = blocks * P2_LANES; j < out_size; j++)
     or_hash_pair(nodes + 8 * (in_size + 2 * j), nodes + 8 * (in_size + 2 * j + 1), nodes + 8 * (out_size + j));
 }
 

@@ -40,6 +40,8 @@ typedef struct {
 } or_rng;
 void or_poseidon2_init(void);
 void or_poseidon2_mix(fp *state24);
+#define P2_LANES 16
+void or_poseidon2_mix_lanes(fp (*state)[P2_LANES]); /* state[24][P2_LANES]: the same permutation on 16 states at once */
 void or_hash_elems_strided(const fp *in, size_t n, size_t stride, uint32_t *digest);
 void or_hash_elem_slice(const fp *in, size_t n, uint32_t *digest);
 void or_hash_ext_elem_slice(const fp4 *in, size_t n, uint32_t *digest);
@@ -58,6 +60,9 @@ void or_batch_bit_reverse(fp *io, size_t count, size_t n);
 void or_zk_shift(fp *io, size_t count, size_t n);
 void or_hash_rows(uint32_t *out_digests, const fp *matrix, size_t rows, size_t cols);
 void or_hash_fold(uint32_t *nodes, size_t in_size, size_t out_size);
+/* one row / one pair at a time through the scalar sponge: the definitions the lane-blocked forms above are tested against */
+void or_hash_rows_scalar(uint32_t *out_digests, const fp *matrix, size_t rows, size_t cols);
+void or_hash_fold_scalar(uint32_t *nodes, size_t in_size, size_t out_size);
 void or_fri_fold(fp *out, const fp *in, const fp4 *mix, size_t out_count);
 void or_batch_evaluate_any(const fp *coeffs, size_t poly_count, size_t n, const uint32_t *which, const fp4 *xs,
                            size_t eval_count, fp4 *out);
@@ -87,6 +92,9 @@ size_t or_circuit_mix_size(const or_circuit *c);
 /* CircuitHal::eval_check: groups = evaluated LDE matrices [cols][4N] in group order accum, code, data. */
 void or_eval_check(const or_circuit *c, fp *check, const fp *const groups[3], const fp *globals, const fp *mix,
                    const fp4 *poly_mix, unsigned po2);
+/* the same, one point at a time with untyped (fp4) values: the definition the lane-blocked or_eval_check is tested against */
+void or_eval_check_scalar(const or_circuit *c, fp *check, const fp *const groups[3], const fp *globals, const fp *mix,
+                          const fp4 *poly_mix, unsigned po2);
 /* verifier-side poly_ext on ext tap evaluations */
 fp4 or_poly_ext(const or_circuit *c, const fp4 *poly_mix, const fp4 *eval_u, const fp *globals, const fp *mix);
 /* synthetic-circuit witness generation / accumulate (the "next row" f1 producer) */

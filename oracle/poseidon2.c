@@ -82,6 +82,73 @@ void or_poseidon2_mix(fp *s) {
   }
 }
 
+/* ---- the same permutation on P2_LANES independent states at once (st[cell][lane]): every field operation is a loop over
+ * lanes that the compiler vectorises.  Used by or_hash_rows / or_hash_fold (hal.c), which hash 16 rows / 16 node pairs per
+ * call; tests/test_oracle_hal.py checks them against the scalar sponge row by row. ---- */
+#define PL P2_LANES
+static inline void lv_acc(fp *restrict acc, const fp *b) {
+  for (int l = 0; l < PL; l++) acc[l] = fp_add(acc[l], b[l]);
+}
+static inline void lv_sbox_rc(fp *io, fp rc) {
+  for (int l = 0; l < PL; l++) io[l] = sbox(fp_add(io[l], rc));
+}
+static void m_ext_lanes(fp (*s)[PL]) {
+  fp sums[4][PL];
+  memset(sums, 0, sizeof sums);
+  for (int c = 0; c < 24; c += 4) {
+    for (int l = 0; l < PL; l++) {
+      fp a = s[c][l], b = s[c + 1][l], cc = s[c + 2][l], d = s[c + 3][l];
+      fp t0 = fp_add(a, b);
+      fp t1 = fp_add(cc, d);
+      fp t2 = fp_add(fp_add(b, b), t1);
+      fp t3 = fp_add(fp_add(d, d), t0);
+      fp t4 = fp_add(fp_add(t1, t1), fp_add(t1, t1));
+      t4 = fp_add(t4, t3);
+      fp t5 = fp_add(fp_add(t0, t0), fp_add(t0, t0));
+      t5 = fp_add(t5, t2);
+      fp t6 = fp_add(t3, t5);
+      fp t7 = fp_add(t2, t4);
+      s[c][l] = t6;
+      s[c + 1][l] = t5;
+      s[c + 2][l] = t7;
+      s[c + 3][l] = t4;
+      sums[0][l] = fp_add(sums[0][l], t6);
+      sums[1][l] = fp_add(sums[1][l], t5);
+      sums[2][l] = fp_add(sums[2][l], t7);
+      sums[3][l] = fp_add(sums[3][l], t4);
+    }
+  }
+  for (int i = 0; i < 24; i++)
+    for (int l = 0; l < PL; l++) s[i][l] = fp_add(s[i][l], sums[i & 3][l]);
+}
+static void m_int_lanes(fp (*s)[PL]) {
+  fp tot[PL];
+  memset(tot, 0, sizeof tot);
+  for (int i = 0; i < 24; i++) lv_acc(tot, s[i]);
+  for (int i = 0; i < 24; i++)
+    for (int l = 0; l < PL; l++) s[i][l] = fp_add(tot[l], fp_mul(DIAG[i], s[i][l]));
+}
+void or_poseidon2_mix_lanes(fp (*s)[P2_LANES]) {
+  or_poseidon2_init();
+  const fp *rc = RC;
+  m_ext_lanes(s);
+  for (int r = 0; r < 4; r++) {
+    for (int i = 0; i < 24; i++) lv_sbox_rc(s[i], rc[i]);
+    rc += 24;
+    m_ext_lanes(s);
+  }
+  for (int r = 0; r < 21; r++) {
+    lv_sbox_rc(s[0], *rc++);
+    m_int_lanes(s);
+  }
+  for (int r = 0; r < 4; r++) {
+    for (int i = 0; i < 24; i++) lv_sbox_rc(s[i], rc[i]);
+    rc += 24;
+    m_ext_lanes(s);
+  }
+}
+#undef PL
+
 /* unpadded_hash over `n` elements read with stride `stride` (stride lets hash_rows walk a column-major matrix). */
 void or_hash_elems_strided(const fp *in, size_t n, size_t stride, uint32_t *digest) {
   fp st[24];

@@ -303,14 +303,16 @@ class Circuit:
         L.or_accumulate(self.h, po2, _p(accum), _p(u32(code)), _p(u32(data)), _p(u32(mix)), _p(u32(noise)), zk_rows)
         return accum
 
-    def eval_check(self, po2, groups, globals_, mix, poly_mix):
+    def eval_check(self, po2, groups, globals_, mix, poly_mix, scalar=False):
+        """scalar=True: the one-point-at-a-time definition (or_eval_check_scalar); default: the lane-blocked typed form"""
         n = 1 << po2
         check = np.empty(16 * n, dtype=np.uint32)
         gs = [u32(g) for g in groups]
         arr = (C.c_void_p * 3)(*[g.ctypes.data for g in gs])
-        L = lib()
-        L.or_eval_check.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint]
-        L.or_eval_check(self.h, _p(check), arr, _p(u32(globals_)), _p(u32(mix)), _p(u32(poly_mix)), po2)
+        fn = lib().or_eval_check_scalar if scalar else lib().or_eval_check
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint]
+        fn.restype = None
+        fn(self.h, _p(check), arr, _p(u32(globals_)), _p(u32(mix)), _p(u32(poly_mix)), po2)
         return check
 
     def prove(self, po2, code, data, globals_, accum_noise, zk_rows, timings=None):

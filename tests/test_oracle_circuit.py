@@ -1,0 +1,32 @@
+"""The oracle's two forms of CircuitHal::eval_check agree bit for bit: the one-point-at-a-time definition (every value an
+ext element) and the lane-blocked, statically typed, slot-recycling form that the CPU baseline runs (oracle/circuit.c)."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+from zeth_b200 import synth_circuit as S
+
+P = 15 * (1 << 27) + 1
+
+
+@pytest.mark.parametrize("mk,po2", [
+    (S.circuit_tiny, 1), (S.circuit_tiny, 2), (S.circuit_tiny, 5), (S.circuit_small, 3), (S.circuit_small, 6),
+    (S.circuit_mux_small, 4), (S.circuit_mux_small, 7), (S.circuit_planning, 5), (S.circuit_rv32im_scale, 4),
+])
+def test_lane_blocked_eval_check_equals_the_scalar_definition(mk, po2):
+    O.build()
+    sc = mk()
+    oc = O.Circuit(sc.blob)
+    rng = np.random.default_rng(0xB2 + po2)
+    n = 1 << po2
+    wa, wc, wd = sc.group_sizes
+    # arbitrary (not constraint-satisfying) inputs: every op of the program sees generic values, incl. the wrap-around taps
+    groups = [O.to_mont(rng.integers(0, P, size=max(w, 1) * 4 * n, dtype=np.uint64).astype(np.uint32)) for w in (wa, wc, wd)]
+    glob = O.to_mont(rng.integers(0, P, size=max(sc.globals_size, 1), dtype=np.uint64).astype(np.uint32))
+    mix = O.to_mont(rng.integers(0, P, size=max(sc.mix_size, 1), dtype=np.uint64).astype(np.uint32))
+    poly_mix = O.to_mont(rng.integers(1, P, size=4, dtype=np.uint64).astype(np.uint32))
+    a = oc.eval_check(po2, groups, glob, mix, poly_mix, scalar=True)
+    b = oc.eval_check(po2, groups, glob, mix, poly_mix)
+    assert a.shape == b.shape == (16 * n,)
+    assert np.array_equal(a, b)
+    assert (b < P).all()
