@@ -84,7 +84,7 @@ void or_poseidon2_mix(fp *s) {
 
 /* ---- the same permutation on P2_LANES independent states at once (st[cell][lane]): every field operation is a loop over
  * lanes that the compiler vectorises.  Used by or_hash_rows / or_hash_fold (hal.c), which hash 16 rows / 16 node pairs per
- * call; tests/test_oracle_hal.py checks them against the scalar sponge row by row. ---- */
+ * call; tests/test_oracle_circuit.py checks them against the scalar sponge row by row. ---- */
 #define PL P2_LANES
 static inline void lv_acc(fp *restrict acc, const fp *b) {
   for (int l = 0; l < PL; l++) acc[l] = fp_add(acc[l], b[l]);

@@ -30,3 +30,27 @@ def test_lane_blocked_eval_check_equals_the_scalar_definition(mk, po2):
     assert a.shape == b.shape == (16 * n,)
     assert np.array_equal(a, b)
     assert (b < P).all()
+
+
+def test_lane_blocked_hash_rows_and_hash_fold_equal_the_scalar_sponge():
+    """16 sponges per permutation call (or_hash_rows / or_hash_fold) vs one at a time, incl. ragged row counts, empty rows and
+    a partial last block"""
+    import ctypes as C
+    O.build()
+    L = O.lib()
+    rng = np.random.default_rng(5)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    for rows, cols in ((1, 5), (7, 16), (16, 0), (33, 17), (64, 48), (1000, 192), (4096, 4)):
+        m = rng.integers(0, P, size=max(rows * cols, 1), dtype=np.uint64).astype(np.uint32)
+        a, b = np.zeros(rows * 8, dtype=np.uint32), np.zeros(rows * 8, dtype=np.uint32)
+        L.or_hash_rows(vp(a), vp(m), C.c_size_t(rows), C.c_size_t(cols))
+        L.or_hash_rows_scalar(vp(b), vp(m), C.c_size_t(rows), C.c_size_t(cols))
+        assert np.array_equal(a, b), (rows, cols)
+        if cols:  # and against the Python-level sponge of row 0
+            assert np.array_equal(a[:8], O.hash_elem_slice(m.reshape(cols, rows)[:, 0]))
+    for out in (1, 2, 8, 16, 17, 64, 100, 4096):
+        nodes = rng.integers(0, P, size=8 * 4 * out, dtype=np.uint64).astype(np.uint32)
+        n2 = nodes.copy()
+        L.or_hash_fold(vp(nodes), C.c_size_t(2 * out), C.c_size_t(out))
+        L.or_hash_fold_scalar(vp(n2), C.c_size_t(2 * out), C.c_size_t(out))
+        assert np.array_equal(nodes, n2), out
