@@ -64,20 +64,62 @@ static void evaluate_one(fp *io, size_t n, const fp *tw, unsigned expand_bits) {
   }
 }
 
+/* Few columns (the 4-column check / FRI groups): parallel over the butterflies of each layer instead of over columns, so
+ * that a 4-column transform still uses every host thread.  Same butterflies, same results. */
+static void interpolate_layers_par(fp *io, size_t n, const fp *tw, fp norm) {
+  unsigned bits = bb_log2(n);
+  for (unsigned s = bits; s >= 1; s--) {
+    const size_t half = (size_t)1 << (s - 1), tstep = n >> s;
+#pragma omp parallel for schedule(static)
+    for (size_t j = 0; j < n / 2; j++) {
+      const size_t i = j & (half - 1);
+      fp *p = io + ((j >> (s - 1)) << s);
+      fp a = p[i], b = p[i + half];
+      p[i] = fp_add(a, b);
+      p[i + half] = fp_mul(fp_sub(a, b), tw[i * tstep]);
+    }
+  }
+#pragma omp parallel for schedule(static)
+  for (size_t i = 0; i < n; i++) io[i] = fp_mul(io[i], norm);
+}
+static void evaluate_layers_par(fp *io, size_t n, const fp *tw, unsigned expand_bits) {
+  unsigned bits = bb_log2(n);
+  for (unsigned s = expand_bits + 1; s <= bits; s++) {
+    const size_t half = (size_t)1 << (s - 1), tstep = n >> s;
+#pragma omp parallel for schedule(static)
+    for (size_t j = 0; j < n / 2; j++) {
+      const size_t i = j & (half - 1);
+      fp *p = io + ((j >> (s - 1)) << s);
+      fp a = p[i], b = fp_mul(p[i + half], tw[i * tstep]);
+      p[i] = fp_add(a, b);
+      p[i + half] = fp_sub(a, b);
+    }
+  }
+}
+static int few_columns(size_t count, size_t n) { return count < (size_t)omp_get_max_threads() && n >= 4096; }
+
 void or_batch_interpolate_ntt(fp *io, size_t count, size_t n) {
   unsigned bits = bb_log2(n);
   fp *tw = make_twiddles(bb_rou_rev(bits), n / 2);
   fp norm = fp_inv(fp_from_u32((uint32_t)n));
+  if (few_columns(count, n)) {
+    for (size_t c = 0; c < count; c++) interpolate_layers_par(io + c * n, n, tw, norm);
+  } else {
 #pragma omp parallel for schedule(dynamic)
-  for (size_t c = 0; c < count; c++) interpolate_one(io + c * n, n, tw, norm);
+    for (size_t c = 0; c < count; c++) interpolate_one(io + c * n, n, tw, norm);
+  }
   free(tw);
 }
 
 void or_batch_evaluate_ntt(fp *io, size_t count, size_t n, unsigned expand_bits) {
   unsigned bits = bb_log2(n);
   fp *tw = make_twiddles(bb_rou_fwd(bits), n / 2);
+  if (few_columns(count, n)) {
+    for (size_t c = 0; c < count; c++) evaluate_layers_par(io + c * n, n, tw, expand_bits);
+  } else {
 #pragma omp parallel for schedule(dynamic)
-  for (size_t c = 0; c < count; c++) evaluate_one(io + c * n, n, tw, expand_bits);
+    for (size_t c = 0; c < count; c++) evaluate_one(io + c * n, n, tw, expand_bits);
+  }
   free(tw);
 }
 
@@ -86,12 +128,22 @@ void or_batch_expand_into_evaluate_ntt(fp *out, const fp *in, size_t count, size
   size_t out_n = in_n << expand_bits;
   unsigned bits = bb_log2(out_n);
   fp *tw = make_twiddles(bb_rou_fwd(bits), out_n / 2);
+  if (few_columns(count, out_n)) {
+    for (size_t c = 0; c < count; c++) {
+      fp *o = out + c * out_n;
+      const fp *p = in + c * in_n;
+#pragma omp parallel for schedule(static)
+      for (size_t i = 0; i < out_n; i++) o[i] = p[i >> expand_bits];
+      evaluate_layers_par(o, out_n, tw, expand_bits);
+    }
+  } else {
 #pragma omp parallel for schedule(dynamic)
-  for (size_t c = 0; c < count; c++) {
-    fp *o = out + c * out_n;
-    const fp *p = in + c * in_n;
-    for (size_t i = 0; i < out_n; i++) o[i] = p[i >> expand_bits];
-    evaluate_one(o, out_n, tw, expand_bits);
+    for (size_t c = 0; c < count; c++) {
+      fp *o = out + c * out_n;
+      const fp *p = in + c * in_n;
+      for (size_t i = 0; i < out_n; i++) o[i] = p[i >> expand_bits];
+      evaluate_one(o, out_n, tw, expand_bits);
+    }
   }
   free(tw);
 }

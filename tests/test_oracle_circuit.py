@@ -54,3 +54,27 @@ def test_lane_blocked_hash_rows_and_hash_fold_equal_the_scalar_sponge():
         L.or_hash_fold(vp(nodes), C.c_size_t(2 * out), C.c_size_t(out))
         L.or_hash_fold_scalar(vp(n2), C.c_size_t(2 * out), C.c_size_t(out))
         assert np.array_equal(nodes, n2), out
+
+
+def test_few_column_ntts_parallel_over_butterflies_equal_the_column_parallel_path():
+    """count < host threads and n >= 4096 takes the per-layer parallel path (oracle/hal.c few_columns); the same columns inside
+    a wide batch take the per-column path: identical results, and iNTT / LDE still invert each other"""
+    O.build()
+    nthreads = int(O.lib().or_num_threads())
+    if nthreads < 2:
+        pytest.skip("single host thread: only one path exists")
+    rng = np.random.default_rng(11)
+    n, few = 8192, 1
+    wide = few + nthreads + 1
+    x = rng.integers(0, P, size=wide * n, dtype=np.uint64).astype(np.uint32)
+    a = x[: few * n].copy()
+    O.batch_interpolate_ntt(a, few)
+    b = x.copy()
+    O.batch_interpolate_ntt(b, wide)
+    assert np.array_equal(a, b[: few * n])
+    ea = O.batch_expand_into_evaluate_ntt(a, few, 2)
+    eb = O.batch_expand_into_evaluate_ntt(b, wide, 2)
+    assert np.array_equal(ea, eb[: few * 4 * n])
+    ra = a.copy()
+    O.batch_evaluate_ntt(ra, few, 0)
+    assert np.array_equal(ra, x[: few * n])
