@@ -79,10 +79,11 @@ impl B200Hal {
         Ok(Buffer { hal: self, ptr: p as *mut u32, len: words })
     }
     pub fn copy_from(&self, host: &[u32]) -> Result<Buffer<'_>> {
-        let b = self.alloc(host.len().max(1))?;
+        let mut b = self.alloc(host.len().max(1))?;
         chk(unsafe { sys::b2z_h2d(self.ctx, b.ptr as *mut c_void, host.as_ptr() as *const c_void, 4 * host.len()) })?;
         chk(unsafe { sys::b2z_sync(self.ctx) })?;
-        Ok(Buffer { len: host.len(), ..b })
+        b.len = host.len(); // (a `Drop` type cannot be rebuilt with struct-update syntax)
+        Ok(b)
     }
     // ---- trait Hal (risc0-zkp hal/mod.rs) ----
     pub fn batch_interpolate_ntt(&self, io: &Buffer, count: usize, po2: u32) -> Result<()> {
