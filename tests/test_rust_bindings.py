@@ -94,3 +94,44 @@ def test_safe_wrapper_only_calls_declared_symbols():
     declared = set(re.findall(r"pub fn (b2z_\w+)\(", sysrs))
     used = set(re.findall(r"sys::(b2z_\w+)\(", hal))
     assert used and used <= declared, f"b2z-hal calls undeclared symbols: {sorted(used - declared)}"
+
+
+def test_safe_wrapper_calls_every_symbol_with_the_declared_number_of_arguments():
+    """cargo is not available here, so the cheapest class of compile errors is caught by hand: each `sys::b2z_*(...)` call in
+    b2z-hal passes as many arguments as the `extern "C"` declaration of b2z-sys takes"""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sysrs = open(os.path.join(root, "bindings", "rust", "b2z-sys", "src", "lib.rs")).read()
+    hal = open(os.path.join(root, "bindings", "rust", "b2z-hal", "src", "lib.rs")).read()
+    decl = {}
+    for m in re.finditer(r"pub fn (b2z_\w+)\((.*?)\)\s*(->\s*[^;]+)?;", sysrs, re.S):
+        decl[m.group(1)] = len([a for a in m.group(2).split(",") if a.strip()])
+
+    def split_top(s):
+        out, depth, cur = [], 0, ""
+        for ch in s:
+            depth += ch in "([{"
+            depth -= ch in ")]}"
+            if ch == "," and depth == 0:
+                out.append(cur)
+                cur = ""
+            else:
+                cur += ch
+        if cur.strip():
+            out.append(cur)
+        return out
+
+    calls = 0
+    for m in re.finditer(r"sys::(b2z_\w+)\(", hal):
+        i = j = m.end()
+        depth = 1
+        while depth:
+            depth += hal[j] == "("
+            depth -= hal[j] == ")"
+            j += 1
+        assert decl.get(m.group(1)) == len(split_top(hal[i:j - 1])), m.group(1)
+        calls += 1
+    assert calls >= 40
+    # a type that implements Drop cannot be rebuilt with struct-update syntax (E0509)
+    assert not re.search(r"\.\.\s*b\s*\}", hal)
