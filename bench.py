@@ -185,7 +185,7 @@ def cpu_reference_run(steps: int, warmup: int, circuit: str = "rv32im_scale"):
     cycles = (1 << po2) * len(ts)
     value = cycles / sum(ts)
     sample = (f"{len(ts)} x po2={po2} segment(s) of the {sc.name.rstrip('_')} circuit (W=256, {sc.n_steps} steps), {sum(ts):.1f} s on "
-              f"{cores} host threads (OpenMP)")
+              f"{cores} host threads (OpenMP, {O.isa()} build of the oracle)")
     return value, cores, sample, 1e3 * sum(ts) / len(ts), po2
 
 

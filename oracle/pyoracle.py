@@ -17,18 +17,39 @@ P = 15 * (1 << 27) + 1
 
 
 def build(force: bool = False) -> str:
+    """liboracle.so (x86-64-v3, AVX2) and liboracle_v4.so (x86-64-v4, AVX-512) from the same sources"""
     so = os.path.join(_HERE, "liboracle.so")
     srcs = [os.path.join(_HERE, f) for f in ("bb.c", "poseidon2.c", "hal.c", "circuit.c", "zkp.c", "bb.h", "oracle.h", "poseidon2_consts.h",
                                               "../include/protocol_params.h")]
-    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-        subprocess.check_call(["make", "-C", _HERE, "-s", "liboracle.so"])
+    for name in ("liboracle.so", "liboracle_v4.so"):
+        out = os.path.join(_HERE, name)
+        if force or not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
+            subprocess.check_call(["make", "-C", _HERE, "-s", name] + (["-B"] if force else []))
     return so
+
+
+def isa() -> str:
+    """Which build lib() loads on this host: 'x86-64-v4' when the CPU has the AVX-512 subsets of that level, else 'x86-64-v3'."""
+    if os.environ.get("B2Z_ORACLE_ISA", "") == "v3":
+        return "x86-64-v3"
+    try:
+        flags = set()
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("flags"):
+                flags = set(line.split(":", 1)[1].split())
+                break
+        if {"avx512f", "avx512dq", "avx512bw", "avx512vl", "avx512cd"} <= flags:
+            return "x86-64-v4"
+    except OSError:
+        pass
+    return "x86-64-v3"
 
 
 def lib():
     global _LIB
     if _LIB is None:
-        so = os.path.join(_HERE, "liboracle.so")
+        name = "liboracle_v4.so" if isa() == "x86-64-v4" else "liboracle.so"
+        so = os.path.join(_HERE, name)
         if not os.path.exists(so):
             build()
         _LIB = C.CDLL(so)
