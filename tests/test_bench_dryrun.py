@@ -83,34 +83,39 @@ class _Session:
         pass
 
 
-def test_block_workload_glue_runs_end_to_end_with_a_mocked_gpu(monkeypatch, capsys):
+class _Event:
+    def __init__(self, enable_timing=False):
+        pass
+
+    def record(self, *a):
+        pass
+
+    def elapsed_time(self, other):
+        return 5.0
+
+
+def _mock_gpu_layer(setattr_):
+    """replace everything of torch.cuda / zeth_b200.hal that bench.run_block_workload touches (setattr_(obj, name, value))"""
     from zeth_b200 import hal as H
     cpu = torch.device("cpu")
     real_device = torch.device
-    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
-    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
-    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
-    monkeypatch.setattr(torch.cuda, "empty_cache", lambda: None)
-    monkeypatch.setattr(torch.cuda, "get_device_properties", lambda d: types.SimpleNamespace(total_memory=180 << 30))
+    setattr_(torch.cuda, "is_available", lambda: True)
+    setattr_(torch.cuda, "set_device", lambda d: None)
+    setattr_(torch.cuda, "synchronize", lambda *a: None)
+    setattr_(torch.cuda, "empty_cache", lambda: None)
+    setattr_(torch.cuda, "get_device_properties", lambda d: types.SimpleNamespace(total_memory=180 << 30))
+    setattr_(torch.cuda, "Event", _Event)
+    setattr_(torch.cuda, "Stream", lambda device=None: types.SimpleNamespace(cuda_stream=0))
+    setattr_(torch, "device", lambda *a, **k: cpu if (a and a[0] == "cuda") else real_device(*a, **k))
+    setattr_(torch.Tensor, "pin_memory", lambda self: self)
+    setattr_(H, "Session", _Session)
+    setattr_(H.Receipt, "assemble", staticmethod(lambda circuit, seals, journal=b"": types.SimpleNamespace(close=lambda: None)))
+    setattr_(bench, "kernel_rooflines", lambda *a, **k: ({"bound": "hbm", "frac": 0.1}, []))
+    setattr_(bench, "cpu_reference_run", lambda steps, warmup, circuit="x": (1.0, 1, "mock", 1.0, 6))
 
-    class _Event:
-        def __init__(self, enable_timing=False):
-            pass
 
-        def record(self, *a):
-            pass
-
-        def elapsed_time(self, other):
-            return 5.0
-
-    monkeypatch.setattr(torch.cuda, "Event", _Event)
-    monkeypatch.setattr(torch.cuda, "Stream", lambda device=None: types.SimpleNamespace(cuda_stream=0))
-    monkeypatch.setattr(torch, "device", lambda *a, **k: cpu if (a and a[0] == "cuda") else real_device(*a, **k))
-    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
-    monkeypatch.setattr(H, "Session", _Session)
-    monkeypatch.setattr(H.Receipt, "assemble", staticmethod(lambda circuit, seals, journal=b"": types.SimpleNamespace(close=lambda: None)))
-    monkeypatch.setattr(bench, "kernel_rooflines", lambda *a, **k: ({"bound": "hbm", "frac": 0.1}, []))
-    monkeypatch.setattr(bench, "cpu_reference_run", lambda steps, warmup, circuit="x": (1.0, 1, "mock", 1.0, 6))
+def test_block_workload_glue_runs_end_to_end_with_a_mocked_gpu(monkeypatch, capsys):
+    _mock_gpu_layer(monkeypatch.setattr)
     monkeypatch.delenv("WORLD_SIZE", raising=False)
     monkeypatch.delenv("RANK", raising=False)
     args = argparse.Namespace(gpus=1, steps=3, warmup=1, workload="block", circuit="planning", po2=6, segments_per_step=2, in_flight=2,
@@ -123,3 +128,49 @@ def test_block_workload_glue_runs_end_to_end_with_a_mocked_gpu(monkeypatch, caps
     assert cfg["receipt_verified_segments"] == 4 and cfg["segment_latency_ms"]["max"] == 14.0 and len(cfg["rank_prove_ms"]) == 1
     assert line["e2e"]["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] > 0 and line["gpu_launches"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["roofline"]["bound"] == "hbm"
+
+
+def _rank_main(rank, world, port, q):
+    import io
+    import os
+    import sys
+    import torch.distributed as dist
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK="0", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    _mock_gpu_layer(setattr)
+    bench._init_dist = lambda local_rank: dist.init_process_group("gloo", rank=rank, world_size=world)
+    args = argparse.Namespace(gpus=world, steps=3, warmup=1, workload="block", circuit="planning", po2=6, segments_per_step=3, in_flight=2,
+                              impl="b2z", no_cpu_baseline=True)
+    out, real = io.StringIO(), sys.stdout
+    sys.stdout = out
+    try:
+        rc = bench.run_block_workload(args)
+    finally:
+        sys.stdout = real
+    q.put((rank, rc, out.getvalue()))
+
+
+def test_block_workload_glue_on_two_ranks_over_gloo():
+    """the N > 1 branches of the same glue: table broadcast, warmed gathers, prove_sharded (ragged shares: 9 segments over 2
+    ranks), per-rank time gather, the e2e gather; rank 0 alone prints the line"""
+    import socket
+    import torch.multiprocessing as mp
+    sock = socket.socket()
+    sock.bind(("127.0.0.1", 0))
+    port = sock.getsockname()[1]
+    sock.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict()
+    for _ in range(2):
+        rank, rc, text = q.get(timeout=180)
+        got[rank] = (rc, text)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got[0][0] == 0 and got[1][0] == 0 and got[1][1].strip() == ""
+    line = json.loads(got[0][1].strip().splitlines()[-1])
+    assert line["n_gpus"] == 2 and line["config"]["segments_total"] == 9 and len(line["config"]["rank_prove_ms"]) == 2
+    assert line["config"]["segments_reassigned_across_ranks"] == 0 and line["e2e"]["value"] > 0 and line["cpu_baseline"] is None
