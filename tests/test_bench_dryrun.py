@@ -66,8 +66,12 @@ class _Session:
         self.hals, self.circuit, self.in_flight, self.L, self.h = [_Hal()], _Circuit(), in_flight, _Lib(), None
         self.proved = []
 
+    fail_on_call = 0  # (tests) the N-th prove call of this process raises once, like a device that drops out
+
     def prove(self, segments, journal=b""):
         self.proved.append([s["index"] for s in segments])
+        if len(self.proved) == _Session.fail_on_call:
+            raise RuntimeError("segment 0: device lost")
         return _Receipt(len(segments), 40)
 
     def set_control_root(self, po2, root):
@@ -130,13 +134,15 @@ def test_block_workload_glue_runs_end_to_end_with_a_mocked_gpu(monkeypatch, caps
     assert line["cpu_baseline"]["kind"] == "port" and line["roofline"]["bound"] == "hbm"
 
 
-def _rank_main(rank, world, port, q):
+def _rank_main(rank, world, port, q, fail_rank=-1):
     import io
     import os
     import sys
     import torch.distributed as dist
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK="0", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     _mock_gpu_layer(setattr)
+    if rank == fail_rank:
+        _Session.fail_on_call = 2  # call 1 = the warm-up, call 2 = this rank's timed share
     bench._init_dist = lambda local_rank: dist.init_process_group("gloo", rank=rank, world_size=world)
     args = argparse.Namespace(gpus=world, steps=3, warmup=1, workload="block", circuit="planning", po2=6, segments_per_step=3, in_flight=2,
                               impl="b2z", no_cpu_baseline=True)
@@ -149,9 +155,7 @@ def _rank_main(rank, world, port, q):
     q.put((rank, rc, out.getvalue()))
 
 
-def test_block_workload_glue_on_two_ranks_over_gloo():
-    """the N > 1 branches of the same glue: table broadcast, warmed gathers, prove_sharded (ragged shares: 9 segments over 2
-    ranks), per-rank time gather, the e2e gather; rank 0 alone prints the line"""
+def _run_two_ranks(fail_rank=-1):
     import socket
     import torch.multiprocessing as mp
     sock = socket.socket()
@@ -160,7 +164,7 @@ def test_block_workload_glue_on_two_ranks_over_gloo():
     sock.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, q, fail_rank)) for r in range(2)]
     for p in procs:
         p.start()
     got = dict()
@@ -170,6 +174,22 @@ def test_block_workload_glue_on_two_ranks_over_gloo():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+    return got
+
+
+def test_a_rank_that_fails_its_timed_share_is_covered_by_the_other_rank():
+    """rank 1's session call raises once: its 4 segments are regenerated and proved on rank 0 inside the timed region, the job
+    still completes, and the line says how many segments moved"""
+    got = _run_two_ranks(fail_rank=1)
+    assert got[0][0] == 0 and got[1][0] == 0
+    line = json.loads(got[0][1].strip().splitlines()[-1])
+    assert line["config"]["segments_total"] == 9 and line["config"]["segments_reassigned_across_ranks"] == 4
+
+
+def test_block_workload_glue_on_two_ranks_over_gloo():
+    """the N > 1 branches of the same glue: table broadcast, warmed gathers, prove_sharded (ragged shares: 9 segments over 2
+    ranks), per-rank time gather, the e2e gather; rank 0 alone prints the line"""
+    got = _run_two_ranks()
     assert got[0][0] == 0 and got[1][0] == 0 and got[1][1].strip() == ""
     line = json.loads(got[0][1].strip().splitlines()[-1])
     assert line["n_gpus"] == 2 and line["config"]["segments_total"] == 9 and len(line["config"]["rank_prove_ms"]) == 2
