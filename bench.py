@@ -422,7 +422,7 @@ def run_segment_workload(args):
                         "achieved_gbs": bytes_in / ms_in / 1e6, "frac_hbm": bytes_in / ms_in / 1e6 / hbm})
         del lde, dig, tmp
         if not args.no_cpu_baseline and world == 1:  # reported at N = 1 only
-            v, cores, sample, _, _ = cpu_reference_run(1, 0, args.circuit)
+            v, cores, sample, _, _ = cpu_reference_run(2, 0, args.circuit)  # ~10-30 s of CPU work
             cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "host": host_info()}
 
     if rank == 0:
@@ -684,7 +684,7 @@ def run_block_workload(args):
         roofline, kernels = kernel_rooflines(hal0, circuit, sc, po2, one, stream, dev)
         del one
         if not args.no_cpu_baseline and world == 1:
-            v, cores, sample, _, _ = cpu_reference_run(1, 0, args.circuit)
+            v, cores, sample, _, _ = cpu_reference_run(2, 0, args.circuit)  # ~10-30 s of CPU work
             cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "host": host_info()}
 
     if rank == 0:
